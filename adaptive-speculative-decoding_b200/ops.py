@@ -1,0 +1,79 @@
+"""Torch-tensor front ends of the CUDA entry points (device pointers + current stream only;
+all arithmetic happens in libasd_b200.so)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from ._lib import AsdError, check, lib
+
+NUM_FEATURES = 6
+FEATURE_NAMES = ("lse", "p_max", "margin", "entropy", "logprob_draft_token", "logprob_resampled_token")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class RejectionSampler:
+    """Owns the zero-initialised workspace of ``asd_reject_sample`` for fixed (B, k)."""
+
+    def __init__(self, B: int, k: int, device="cuda"):
+        self.B, self.k = B, k
+        self.device = torch.device(device)
+        nbytes = lib().asd_reject_sample_workspace_bytes(B, k)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.accept_mask = torch.empty(B, k, dtype=torch.uint8, device=self.device)
+        self.accepted_len = torch.empty(B, dtype=torch.int32, device=self.device)
+        self.out_tokens = torch.empty(B, k + 1, dtype=torch.int32, device=self.device)
+        self.out_logprobs = torch.empty(B, k + 1, dtype=torch.float32, device=self.device)
+        self.features = torch.empty(B, k + 1, NUM_FEATURES, dtype=torch.float32, device=self.device)
+
+    def __call__(self, target_logits: torch.Tensor, draft_logits: Optional[torch.Tensor],
+                 draft_tokens: torch.Tensor, u_accept: torch.Tensor, u_resid: torch.Tensor, temperature: float):
+        B, k = self.B, self.k
+        if not target_logits.is_cuda:
+            raise AsdError("asd_reject_sample needs CUDA tensors (no CPU fallback)")
+        V = target_logits.shape[-1]
+        assert target_logits.dtype == torch.float32 and target_logits.is_contiguous()
+        assert target_logits.numel() == B * (k + 1) * V
+        if draft_logits is not None:
+            assert draft_logits.dtype == torch.float32 and draft_logits.is_contiguous()
+            assert draft_logits.numel() == B * k * V
+        assert draft_tokens.dtype == torch.int32 and draft_tokens.numel() == B * k
+        assert u_accept.dtype == torch.float64 and u_accept.numel() == B * k
+        assert u_resid.dtype == torch.float64 and u_resid.numel() == B
+        with torch.cuda.device(self.device):
+            rc = lib().asd_reject_sample(
+                target_logits.data_ptr(), 0 if draft_logits is None else draft_logits.data_ptr(),
+                draft_tokens.data_ptr(), u_accept.data_ptr(), u_resid.data_ptr(), B, k, V, float(temperature),
+                self.accept_mask.data_ptr(), self.accepted_len.data_ptr(), self.out_tokens.data_ptr(),
+                self.out_logprobs.data_ptr(), self.features.data_ptr(), self.workspace.data_ptr(), _stream())
+        check(rc, "asd_reject_sample")
+        return dict(accept_mask=self.accept_mask, accepted_len=self.accepted_len, out_tokens=self.out_tokens,
+                    out_logprobs=self.out_logprobs, features=self.features)
+
+
+def reject_sample_host(target_logits, draft_logits, draft_tokens, u_accept, u_resid, temperature):
+    """numpy (HOST) buffers in and out through ``asd_reject_sample_host``: the call a non-torch
+    integrator would make; copies happen inside the library."""
+    import numpy as np
+    tl = np.ascontiguousarray(target_logits, dtype=np.float32)
+    B, k1, V = tl.shape
+    k = k1 - 1
+    dl = None if draft_logits is None else np.ascontiguousarray(draft_logits, dtype=np.float32)
+    dt = np.ascontiguousarray(draft_tokens, dtype=np.int32).reshape(B, k)
+    ua = np.ascontiguousarray(u_accept, dtype=np.float64).reshape(B, k)
+    ur = np.ascontiguousarray(u_resid, dtype=np.float64).reshape(B)
+    out = dict(accept_mask=np.zeros((B, k), np.uint8), accepted_len=np.zeros(B, np.int32),
+               out_tokens=np.zeros((B, k + 1), np.int32), out_logprobs=np.zeros((B, k + 1), np.float32),
+               features=np.zeros((B, k + 1, NUM_FEATURES), np.float32))
+    rc = lib().asd_reject_sample_host(tl.ctypes.data, None if dl is None else dl.ctypes.data, dt.ctypes.data,
+                                      ua.ctypes.data, ur.ctypes.data, B, k, V, float(temperature),
+                                      out["accept_mask"].ctypes.data, out["accepted_len"].ctypes.data,
+                                      out["out_tokens"].ctypes.data, out["out_logprobs"].ctypes.data,
+                                      out["features"].ctypes.data)
+    check(rc, "asd_reject_sample_host")
+    return out
