@@ -41,6 +41,8 @@ def lib() -> ctypes.CDLL:
         "asd_stop_rule": (i32, [vp, vp, i32, i32, f64, i32, f64, f64, vp, vp, vp]),
         "asd_stop_rule_host": (i32, [vp, vp, i32, f64, i32, f64, f64, vp]),
         "asd_bayesian_adjustment_host": (f64, [f64, f64, f64, f64]),
+        "asd_linear_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "asd_linear_plan": (i32, [i32, i32, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)

@@ -1,0 +1,385 @@
+// Weight-streaming bf16 GEMM for the verify / draft forward:  Y[m, n] = sum_k X[m, k] * W[n, k].
+//
+// The verify step has few rows (M = B*(k+1) = 16..256 tokens) and huge weights, so it is bound by
+// streaming W from HBM once.  B200-first design ("swap-AB"):
+//   * the WEIGHT tile (128 rows of W, K-major) is the tcgen05 A operand (UMMA M = 128), the token
+//     tile (MT = M rounded up to 16, <= 256 rows of X) is the B operand (UMMA N = MT): no tensor
+//     work is wasted on padding rows and one TMEM accumulator [128 lanes x MT columns] holds the tile;
+//   * both operands arrive by TMA (128-byte swizzle) into a multi-stage mbarrier ring; W with an
+//     L2 evict-first policy (read exactly once), X with evict-last (re-read by every CTA);
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+//     warps 2..5 = epilogue (tcgen05.ld -> registers -> global);
+//   * grid = (weight tiles, K splits, token tiles); the host picks the split so that all CTAs are
+//     co-resident in ONE wave (2-3 CTAs/SM) - with HBM as the shared bottleneck every CTA then
+//     progresses at the same rate and there is no tail; split-K partials are fp32 slices that the
+//     consumer kernel (add+RMSNorm / RoPE) sums in a fixed order (deterministic, no atomics).
+// Epilogues: fp32 (partials / logits), bf16, and SwiGLU for the gate|up projection whose rows are
+// pre-interleaved (64 gate rows, 64 up rows per tile) so silu(g)*u never round-trips to HBM.
+//
+// Stands behind Stage.generate's model forward, which the reference delegates to vLLM
+// (/root/reference/src/serving/real_model_pipeline.py:98-108,135).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "asd_internal.h"
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace asd {
+
+constexpr int kTileN = 128;       // weight rows per CTA (UMMA M)
+constexpr int kBlockK = 64;       // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kGemmThreads = 192; // 6 warps
+constexpr int kABytes = kTileN * kBlockK * 2;
+
+struct GemmArgs {
+    int M, N, K;        // logical problem
+    int MT;             // token tile (multiple of 16, <= 256)
+    int kblocks;        // ceil(K / 64)
+    int ksplit;
+    int stages;
+    int mode;
+    int ldo;            // leading dimension of the output (elements)
+    int n_valid;        // rows of the output that exist (SwiGLU: ff; else N)
+    void* out;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+
+__global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                                                                const __grid_constant__ CUtensorMap tmap_x,
+                                                                const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem is only guaranteed 16-byte aligned: align the tile ring to 1024 by hand
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = kABytes + a.MT * 128;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + a.stages;
+    uint64_t* tmem_full = empty_bar + a.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* xbuf = reinterpret_cast<float*>(tmem_slot + 4);  // SwiGLU exchange: [2][64][33] floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_n = blockIdx.x, split = blockIdx.y, tile_m = blockIdx.z;
+    const int base = a.kblocks / a.ksplit, rem = a.kblocks % a.ksplit;
+    const int kb0 = split * base + (split < rem ? split : rem);
+    const int nkb = base + (split < rem ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, a.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
+            // Weights do not depend on the upstream kernel: start streaming them before the
+            // programmatic-dependent-launch wait; activations only after it.
+            int pre = nkb < a.stages ? nkb : a.stages;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_expect_tx(&full_bar[kb], stage_bytes);
+                tma_load_2d_hint(smem + (size_t)kb * stage_bytes, &tmap_w, (kb0 + kb) * kBlockK, tile_n * kTileN,
+                                 &full_bar[kb], pol_w);
+            }
+            grid_dep_wait();
+            for (int kb = 0; kb < pre; ++kb)
+                tma_load_2d_hint(smem + (size_t)kb * stage_bytes + kABytes, &tmap_x, (kb0 + kb) * kBlockK,
+                                 tile_m * a.MT, &full_bar[kb], pol_x);
+            int s = pre % a.stages;
+            uint32_t ph = (pre == a.stages) ? 1 : 0;  // parity of the NEXT use of slot s
+            for (int kb = pre; kb < nkb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], stage_bytes);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                tma_load_2d_hint(st, &tmap_w, (kb0 + kb) * kBlockK, tile_n * kTileN, &full_bar[s], pol_w);
+                tma_load_2d_hint(st + kABytes, &tmap_x, (kb0 + kb) * kBlockK, tile_m * a.MT, &full_bar[s], pol_x);
+                if (++s == a.stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = umma_idesc_bf16(kTileN, a.MT);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)  // 16 bf16 = 32 bytes = +2 in the >>4 address field
+                    umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty_bar[s]);
+                if (kb == nkb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (++s == a.stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+        if (nkb == 0 && lane == 0) mbar_arrive(tmem_full);
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;             // accumulator row = weight row inside the tile
+        const int m0 = tile_m * a.MT;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        grid_dep_launch();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (a.mode == GEMM_OUT_SWIGLU) {
+            // rows 0..63 = gate, 64..127 = up of ff index tile_n*64 + (row & 63)
+            const int et = threadIdx.x - 64;      // 0..127 among epilogue threads
+            __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+            for (int c0 = 0; c0 < a.MT; c0 += 32) {
+                uint32_t r[32];
+                if (nkb > 0) {
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = 0;
+                }
+                float* dst = xbuf + (row >> 6) * (64 * 33) + (row & 63) * 33;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(r[i]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // thread et: ff row (et & 63), column half (et >> 6)
+                const int fr = et & 63, ch = (et >> 6) * 16;
+                const int j = tile_n * 64 + fr;
+                const float* g = xbuf + fr * 33 + ch;
+                const float* u = xbuf + 64 * 33 + fr * 33 + ch;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int m = m0 + c0 + ch + i;
+                    if (c0 + ch + i < a.MT && m < a.M && j < a.n_valid)
+                        out[(size_t)m * a.ldo + j] = __float2bfloat16(silu_mul(g[i], u[i]));
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        } else {
+            const int n = tile_n * kTileN + row;
+            for (int c0 = 0; c0 < a.MT; c0 += 32) {
+                uint32_t r[32];
+                if (nkb > 0) {
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = 0;
+                }
+                if (n < a.n_valid) {
+                    if (a.mode == GEMM_OUT_BF16) {
+                        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int m = m0 + c0 + i;
+                            if (c0 + i < a.MT && m < a.M) out[(size_t)m * a.ldo + n] = __float2bfloat16(__uint_as_float(r[i]));
+                        }
+                    } else {  // fp32, one [M, ldo] slice per K split
+                        float* out = static_cast<float*>(a.out) + (size_t)split * a.M * a.ldo;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int m = m0 + c0 + i;
+                            if (c0 + i < a.MT && m < a.M) out[(size_t)m * a.ldo + n] = __uint_as_float(r[i]);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ASD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return set_error("cuTensorMapEncodeTiled unavailable");
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return 0;
+}
+
+// bf16 row-major [rows, cols] matrix, box = {64 cols, box_rows}, 128-byte swizzle, zero OOB fill
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                   uint32_t box_rows) {
+    if (load_encode()) return -1;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * 2) % 16)
+        return set_error("tensor map: base and row stride must be 16-byte aligned");
+    if (box_rows == 0 || box_rows > 256) return set_error("tensor map: box rows must be in [1, 256]");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static int g_num_sms = 0;
+static int g_smem_optin = 0;
+static int g_gemm_attr_set = 0;
+
+static int device_props() {
+    if (g_num_sms) return 0;
+    int dev = 0;
+    ASD_CUDA(cudaGetDevice(&dev));
+    ASD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    ASD_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return 0;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int gemm_token_tile(int M) {
+    if (M <= 256) return round_up(M < 16 ? 16 : M, 16);
+    const int tiles = (M + 255) / 256;
+    return round_up((M + tiles - 1) / tiles, 16);
+}
+
+// Choose the split so that all CTAs fit in one co-resident wave and there are enough bytes in flight.
+int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages) {
+    if (device_props()) return -1;
+    if (M <= 0 || N <= 0 || K <= 0 || (K & 7)) return set_error("gemm: need M, N, K > 0 and K %% 8 == 0");
+    pl->M = M;
+    pl->N = N;
+    pl->K = K;
+    pl->mode = mode;
+    pl->MT = gemm_token_tile(M);
+    pl->m_tiles = (M + pl->MT - 1) / pl->MT;
+    pl->n_tiles = (N + kTileN - 1) / kTileN;
+    pl->kblocks = (K + kBlockK - 1) / kBlockK;
+    const int stage_bytes = kABytes + pl->MT * 128;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + (mode == GEMM_OUT_SWIGLU ? 2 * 64 * 33 * 4 : 0);
+    // residency target: 3 CTAs/SM for small token tiles, 2 for large ones
+    const int ctas_per_sm = pl->MT <= 128 ? 3 : 2;
+    const int budget = (227 * 1024) / ctas_per_sm - fixed - 1024;
+    int stages = budget / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    const int slots = g_num_sms * ctas_per_sm;
+    const int tiles = pl->n_tiles * pl->m_tiles;
+    int ksplit = 1;
+    if (mode != GEMM_OUT_SWIGLU && mode != GEMM_OUT_BF16) {
+        // largest split that keeps every CTA resident, each with >= 4 k-blocks of work
+        ksplit = slots / tiles;
+        if (ksplit < 1) ksplit = 1;
+        const int max_by_k = pl->kblocks / 4 > 0 ? pl->kblocks / 4 : 1;
+        if (ksplit > max_by_k) ksplit = max_by_k;
+        if (ksplit > 16) ksplit = 16;
+    }
+    if (force_ksplit > 0) ksplit = force_ksplit;
+    if (force_stages > 0) stages = force_stages;
+    if ((mode == GEMM_OUT_SWIGLU || mode == GEMM_OUT_BF16) && ksplit != 1)
+        return set_error("gemm: bf16 / SwiGLU epilogues need ksplit == 1");
+    if (ksplit > pl->kblocks) ksplit = pl->kblocks;
+    pl->ksplit = ksplit;
+    pl->stages = stages;
+    pl->smem_bytes = fixed + stages * stage_bytes;
+    if (pl->smem_bytes > g_smem_optin) return set_error("gemm: tile does not fit in shared memory");
+    uint32_t cols = 32;
+    while ((int)cols < pl->MT) cols <<= 1;
+    pl->tmem_cols = cols;
+    return 0;
+}
+
+int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
+                int n_valid, bool pdl, cudaStream_t stream) {
+    if (!g_gemm_attr_set) {
+        if (device_props()) return -1;
+        ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+        g_gemm_attr_set = 1;
+    }
+    GemmArgs a;
+    a.M = pl.M;
+    a.N = pl.N;
+    a.K = pl.K;
+    a.MT = pl.MT;
+    a.kblocks = pl.kblocks;
+    a.ksplit = pl.ksplit;
+    a.stages = pl.stages;
+    a.mode = pl.mode;
+    a.ldo = ldo;
+    a.n_valid = n_valid;
+    a.out = out;
+    a.tmem_cols = pl.tmem_cols;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(pl.n_tiles, pl.ksplit, pl.m_tiles);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = stream;
+    if (pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    ASD_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel, tmap_w, tmap_x, a));
+    count_launch(1);
+    return 0;
+}
+
+}  // namespace asd
+
+// ------------------------------------------------------------------------------------------- C ABI
+#include "../../include/asd_b200.h"
+extern "C" int asd_linear_bf16(const void* x, const void* w, void* out, int M, int N, int K, int out_mode,
+                               int ksplit, int stages, int* ksplit_used, void* stream) {
+    using namespace asd;
+    GemmPlan pl;
+    if (out_mode < 0 || out_mode > 2) return set_error("asd_linear_bf16: bad out_mode");
+    if (gemm_plan(&pl, M, N, K, out_mode, ksplit, stages)) return -1;
+    CUtensorMap tw, tx;
+    if (make_tmap_bf16(&tw, w, N, K, K, 128)) return -1;
+    if (make_tmap_bf16(&tx, x, M, K, K, pl.MT)) return -1;
+    if (ksplit_used) *ksplit_used = pl.ksplit;
+    const int ldo = out_mode == GEMM_OUT_SWIGLU ? N / 2 : N;
+    return gemm_launch(pl, tw, tx, out, ldo, ldo, false, static_cast<cudaStream_t>(stream));
+}
+extern "C" int asd_linear_plan(int M, int N, int K, int out_mode, int* ksplit, int* stages, int* token_tile) {
+    using namespace asd;
+    GemmPlan pl;
+    if (gemm_plan(&pl, M, N, K, out_mode, 0, 0)) return -1;
+    if (ksplit) *ksplit = pl.ksplit;
+    if (stages) *stages = pl.stages;
+    if (token_tile) *token_tile = pl.MT;
+    return 0;
+}

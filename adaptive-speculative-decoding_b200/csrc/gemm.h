@@ -1,0 +1,26 @@
+// Host-side interface of the weight-streaming tcgen05 GEMM (gemm.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace asd {
+
+enum GemmOut { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_SWIGLU = 2 };
+
+struct GemmPlan {
+    int M, N, K, mode;
+    int MT, m_tiles, n_tiles, kblocks, ksplit, stages, smem_bytes;
+    uint32_t tmem_cols;
+};
+
+int gemm_token_tile(int M);
+int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages);
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                   uint32_t box_rows);
+// out: GEMM_OUT_F32 -> float [ksplit][M][ldo]; GEMM_OUT_BF16 -> bf16 [M][ldo];
+// GEMM_OUT_SWIGLU -> bf16 [M][ldo] with N/2 columns (n_valid = ff)
+int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
+                int n_valid, bool pdl, cudaStream_t stream);
+
+}  // namespace asd

@@ -445,6 +445,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
 }
 
 static int g_max_clusters[kMaxSlabs + 1];
+static int g_attr_set = 0;
 
 size_t reject_sample_workspace_bytes(int B, int k) {
     const size_t rows = (size_t)B * (k + 1);
@@ -503,8 +504,14 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (!g_attr_set) {
+        int dev = 0, optin = 0;
+        ASD_CUDA(cudaGetDevice(&dev));
+        ASD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        ASD_CUDA(cudaFuncSetAttribute(reject_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        g_attr_set = 1;
+    }
     if (g_max_clusters[num_slabs] == 0) {
-        ASD_CUDA(cudaFuncSetAttribute(reject_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg.gridDim = dim3(kCluster * 148);
         int n = 0;
         ASD_CUDA(cudaOccupancyMaxActiveClusters(&n, reject_sample_kernel, &cfg));

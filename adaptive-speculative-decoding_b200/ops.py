@@ -77,3 +77,46 @@ def reject_sample_host(target_logits, draft_logits, draft_tokens, u_accept, u_re
                                       out["features"].ctypes.data)
     check(rc, "asd_reject_sample_host")
     return out
+
+
+def linear_bf16(x: torch.Tensor, w: torch.Tensor, out_mode: int = 0, ksplit: int = 0, stages: int = 0):
+    """Y = X @ W^T through ``asd_linear_bf16`` (tcgen05/TMA).  out_mode 0 -> fp32 [M, N] (the K-split
+    slices are summed here, in order, as the fused consumer kernels do); 1 -> bf16 [M, N];
+    2 -> SwiGLU over gate|up-interleaved rows, bf16 [M, N/2]."""
+    assert x.is_cuda and w.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    x, w = x.contiguous(), w.contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    used = ctypes.c_int(0)
+    if out_mode == 0:
+        ks, st, tt = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().asd_linear_plan(M, N, K, 0, ctypes.byref(ks), ctypes.byref(st), ctypes.byref(tt)), "plan")
+        nsl = ksplit if ksplit > 0 else ks.value
+        out = torch.empty(nsl, M, N, dtype=torch.float32, device=x.device)
+    elif out_mode == 1:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+    else:
+        out = torch.empty(M, N // 2, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib().asd_linear_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, out_mode, ksplit, stages,
+                                   ctypes.byref(used), _stream())
+    check(rc, "asd_linear_bf16")
+    if out_mode == 0:
+        assert used.value == out.shape[0]
+        acc = out[0].clone()
+        for s in range(1, out.shape[0]):
+            acc += out[s]
+        return acc
+    return out
+
+
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """[ff, K] gate and up weights -> [2*ceil(ff/64)*64, K] with 64 gate rows then 64 up rows per
+    128-row tile (zero rows pad ff to a multiple of 64): the layout asd_linear_bf16 mode 2 expects."""
+    ff, K = gate_w.shape
+    ffp = (ff + 63) // 64 * 64
+    g = torch.zeros(ffp, K, dtype=gate_w.dtype, device=gate_w.device)
+    u = torch.zeros(ffp, K, dtype=up_w.dtype, device=up_w.device)
+    g[:ff], u[:ff] = gate_w, up_w
+    return torch.stack([g.view(ffp // 64, 64, K), u.view(ffp // 64, 64, K)], dim=1).reshape(2 * ffp, K).contiguous()

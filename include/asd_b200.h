@@ -77,6 +77,22 @@ ASD_API int asd_stop_rule_host(const double* p, const double* C, int L, double l
                        double beta, double* J);
 ASD_API double asd_bayesian_adjustment_host(double p_hat, double n_obs, double alpha, double beta);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weight-streaming linear layer  Y[m, n] = sum_k X[m, k] * W[n, k]  (bf16 in, fp32 accumulate) on
+ * tcgen05/TMEM fed by TMA: the dense contraction of the verify / draft forward that the reference
+ * delegates to vLLM (src/serving/real_model_pipeline.py:98-108,135).
+ *   x bf16 [M, K]; w bf16 [N, K] (torch nn.Linear layout); K % 8 == 0; 16-byte aligned.
+ *   out_mode 0: out fp32 [ksplit_used, M, N] - one slice per K split, the caller (or the fused
+ *               add+RMSNorm / RoPE kernels) sums the slices in order;
+ *   out_mode 1: out bf16 [M, N] (ksplit forced to 1);
+ *   out_mode 2: SwiGLU - w rows interleaved per 128-row tile as 64 gate rows then 64 up rows;
+ *               out bf16 [M, N/2] = silu(gate) * up.
+ *   ksplit / stages: 0 = let the library choose (single co-resident wave).
+ */
+ASD_API int asd_linear_bf16(const void* x, const void* w, void* out, int M, int N, int K, int out_mode, int ksplit,
+                    int stages, int* ksplit_used, void* stream);
+ASD_API int asd_linear_plan(int M, int N, int K, int out_mode, int* ksplit, int* stages, int* token_tile);
+
 #ifdef __cplusplus
 }
 #endif

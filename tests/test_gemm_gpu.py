@@ -1,0 +1,60 @@
+"""tcgen05/TMA weight-streaming GEMM against a plain PyTorch fp32 reference of the same op.
+Inputs are bf16 and products are exact in fp32, so only the fp32 summation order differs:
+tolerance 1e-3 relative to the row scale (stated per test)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_fp32(x, w):
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return x.float() @ w.float().t()
+
+
+@pytest.mark.parametrize("M,N,K,ksplit,stages", [
+    (16, 128, 64, 1, 2), (16, 256, 512, 1, 0), (96, 1280, 5120, 0, 0), (96, 5120, 5120, 0, 0),
+    (5, 384, 896, 0, 0), (16, 4608, 3584, 0, 0), (48, 640, 1024, 3, 3), (96, 1000, 712, 0, 0),
+    (128, 512, 2048, 4, 0), (200, 384, 1536, 2, 0), (256, 256, 1024, 0, 0), (300, 384, 512, 0, 0),
+    (576, 1024, 1024, 0, 0), (1, 152064, 896, 0, 0)])
+def test_linear_fp32(M, N, K, ksplit, stages):
+    import torch
+    from asd_b200.ops import linear_bf16
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    y = linear_bf16(x, w, 0, ksplit, stages)
+    torch.cuda.synchronize()
+    ref = ref_fp32(x, w)
+    scale = ref.abs().max().item()
+    assert torch.isfinite(y).all()
+    assert (y - ref).abs().max().item() <= 1e-3 * scale, ((y - ref).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(96, 512, 1024), (16, 1152, 896), (33, 130, 256)])
+def test_linear_bf16_out(M, N, K):
+    import torch
+    from asd_b200.ops import linear_bf16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    y = linear_bf16(x, w, 1)
+    ref = ref_fp32(x, w)
+    scale = ref.abs().max().item()
+    assert (y.float() - ref).abs().max().item() <= 8e-3 * scale   # bf16 output rounding (2^-8)
+
+
+@pytest.mark.parametrize("M,ff,K", [(96, 256, 512), (16, 4864, 896), (40, 200, 256), (288, 512, 512)])
+def test_linear_swiglu(M, ff, K):
+    import torch
+    from asd_b200.ops import interleave_gate_up, linear_bf16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    wg = (torch.randn(ff, K, device="cuda", generator=g) * 0.05).bfloat16()
+    wu = (torch.randn(ff, K, device="cuda", generator=g) * 0.05).bfloat16()
+    w = interleave_gate_up(wg, wu)
+    y = linear_bf16(x, w, 2)[:, :ff]
+    gr, ur = ref_fp32(x, wg), ref_fp32(x, wu)
+    ref = torch.nn.functional.silu(gr) * ur
+    scale = ref.abs().max().item()
+    assert (y.float() - ref).abs().max().item() <= 8e-3 * scale
