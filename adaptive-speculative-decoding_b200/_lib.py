@@ -15,6 +15,14 @@ class AsdError(RuntimeError):
     pass
 
 
+class ModelConfigC(ctypes.Structure):
+    """mirror of ``asd_model_config`` (include/asd_b200.h)"""
+    _fields_ = [("hidden", ctypes.c_int), ("n_layers", ctypes.c_int), ("n_heads", ctypes.c_int),
+                ("n_kv_heads", ctypes.c_int), ("head_dim", ctypes.c_int), ("ffn", ctypes.c_int),
+                ("vocab", ctypes.c_int), ("rms_eps", ctypes.c_float), ("max_tokens", ctypes.c_int),
+                ("page_size", ctypes.c_int), ("tp_rank", ctypes.c_int), ("tp_size", ctypes.c_int)]
+
+
 def library_path() -> str:
     return os.path.join(_HERE, "libasd_b200.so")
 
@@ -43,6 +51,15 @@ def lib() -> ctypes.CDLL:
         "asd_bayesian_adjustment_host": (f64, [f64, f64, f64, f64]),
         "asd_linear_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
         "asd_linear_plan": (i32, [i32, i32, i32, i32, vp, vp, vp]),
+        "asd_engine_create": (vp, [vp]),
+        "asd_engine_destroy": (None, [vp]),
+        "asd_engine_set_layer": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "asd_engine_set_globals": (i32, [vp, vp, vp, vp, vp]),
+        "asd_engine_kv_pool_bytes": (sz, [vp, i32]),
+        "asd_engine_set_kv": (i32, [vp, vp, i32, vp, i32, i32]),
+        "asd_engine_set_allreduce": (i32, [vp, vp, vp]),
+        "asd_engine_set_option": (i32, [vp, c.c_char_p, i32]),
+        "asd_engine_forward": (i32, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, c.c_longlong, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)

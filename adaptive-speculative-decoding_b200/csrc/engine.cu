@@ -1,0 +1,338 @@
+// Qwen2-family forward engine: one opaque handle per (model, tensor-parallel rank).
+// asd_engine_forward runs embedding -> L x [RMSNorm, QKV GEMM, RoPE + paged-KV append, attention,
+// O GEMM, add+RMSNorm, gate|up GEMM with fused SwiGLU, down GEMM, add+RMSNorm] -> lm_head GEMM on
+// the caller's stream with no host synchronisation (CUDA-graph capturable).
+//
+// This is the slot the reference fills with vllm.LLM(...).generate
+// (/root/reference/src/serving/real_model_pipeline.py:98-108,135; Stage listing in
+// docs/guides/RESEARCH_PROTOCOL.md:233-304).  Tensor parallelism mirrors what vLLM does for the
+// reference's `tensor_parallel_size` (configs/qwen3_models.yaml:10,22,34,46): column-parallel
+// QKV / gate|up, row-parallel O / down, one all-reduce after each row-parallel GEMM.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/asd_b200.h"
+#include "asd_internal.h"
+#include "gemm.h"
+#include "layers.h"
+
+namespace asd {
+
+typedef int (*allreduce_fn_t)(const void* send, void* recv, size_t count, int dtype, int op, void* comm,
+                              cudaStream_t stream);
+
+struct Layer {
+    const __nv_bfloat16 *wqkv = nullptr, *bqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr,
+                        *ln1 = nullptr, *ln2 = nullptr;
+    CUtensorMap t_qkv, t_o, t_gu, t_down;
+};
+
+struct Plans {
+    GemmPlan qkv, o, gu, down;
+    CUtensorMap x_norm, x_attn, x_act;
+};
+
+struct Engine {
+    asd_model_config c;
+    int nqkv, qdim, ffp;  // local dims
+    std::vector<Layer> layers;
+    const __nv_bfloat16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+    const float* inv_freq = nullptr;
+    CUtensorMap t_lm;
+    __nv_bfloat16* kv_pool = nullptr;
+    size_t kv_half = 0;  // elements of one K (or V) pool of one layer
+    const int* page_table = nullptr;
+    int num_pages = 0, max_seqs = 0, max_pages = 0;
+    // owned activations
+    float *resid = nullptr, *part = nullptr, *o_part = nullptr, *ml_part = nullptr;
+    __nv_bfloat16 *xnorm = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *xsel = nullptr;
+    size_t part_floats = 0, o_part_floats = 0;
+    std::unordered_map<int, Plans> plans;
+    std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
+    // options
+    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16;
+    void* comm = nullptr;
+    allreduce_fn_t allreduce = nullptr;
+};
+
+static int ensure_plans(Engine* e, int M, Plans** out) {
+    auto it = e->plans.find(M);
+    if (it != e->plans.end()) {
+        *out = &it->second;
+        return 0;
+    }
+    Plans p;
+    const int h = e->c.hidden;
+    if (gemm_plan(&p.qkv, M, e->nqkv, h, GEMM_OUT_F32, e->force_ksplit, e->force_stages)) return -1;
+    if (gemm_plan(&p.o, M, h, e->qdim, GEMM_OUT_F32, e->force_ksplit, e->force_stages)) return -1;
+    if (gemm_plan(&p.gu, M, 2 * e->ffp, h, GEMM_OUT_SWIGLU, 0, e->force_stages)) return -1;
+    if (gemm_plan(&p.down, M, h, e->c.ffn, GEMM_OUT_F32, e->force_ksplit, e->force_stages)) return -1;
+    const size_t need = (size_t)M * std::max(std::max((size_t)p.qkv.ksplit * e->nqkv, (size_t)p.o.ksplit * h),
+                                             (size_t)p.down.ksplit * h);
+    if (need > e->part_floats) return set_error("engine: split-K workspace too small for M = %d", M);
+    if (make_tmap_bf16(&p.x_norm, e->xnorm, M, h, h, p.qkv.MT)) return -1;
+    if (make_tmap_bf16(&p.x_attn, e->attn, M, e->qdim, e->qdim, p.o.MT)) return -1;
+    if (make_tmap_bf16(&p.x_act, e->act, M, e->c.ffn, e->c.ffn, p.down.MT)) return -1;
+    auto r = e->plans.emplace(M, p);
+    *out = &r.first->second;
+    return 0;
+}
+
+static int tp_allreduce(Engine* e, float* buf, int nslices, size_t slice_stride, size_t n, cudaStream_t s) {
+    if (launch_reduce_slices(buf, nslices, slice_stride, n, s)) return -1;
+    const int rc = e->allreduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, s);
+    if (rc != 0) return set_error("engine: all-reduce failed with ncclResult %d", rc);
+    return 0;
+}
+
+static int forward(Engine* e, const int* tokens, const int* positions, const int* token_slot, int M, const int* cu_q,
+                   const int* seq_slot, int nseq, int max_qlen, int max_kv_len, const int* logit_rows,
+                   int n_logit_rows, float* logits_out, long long logits_ld, cudaStream_t s) {
+    const asd_model_config& c = e->c;
+    if (M <= 0) return 0;
+    if (M > c.max_tokens) return set_error("engine: M = %d exceeds max_tokens = %d", M, c.max_tokens);
+    if (!e->embed || !e->kv_pool || !e->inv_freq) return set_error("engine: weights / KV pool not set");
+    for (auto& L : e->layers)
+        if (!L.wqkv) return set_error("engine: a layer has no weights");
+    Plans* P = nullptr;
+    if (ensure_plans(e, M, &P)) return -1;
+    const int h = c.hidden, nh = c.n_heads, nkv = c.n_kv_heads, hd = c.head_dim;
+    const bool tp = c.tp_size > 1;
+    if (tp && !e->allreduce) return set_error("engine: tp_size > 1 but no all-reduce installed");
+
+    // attention split selection: enough CTAs to fill the machine, bounded workspace
+    int nsplit = (2 * 148 + nseq * nkv - 1) / (nseq * nkv);
+    const int max_by_len = (max_kv_len + 63) / 64;
+    if (nsplit > max_by_len) nsplit = max_by_len;
+    if (nsplit > e->max_attn_splits) nsplit = e->max_attn_splits;
+    if (nsplit < 1) nsplit = 1;
+    int split_keys = ((max_kv_len + nsplit - 1) / nsplit + 63) / 64 * 64;
+    if (split_keys < 64) split_keys = 64;
+    const int nsplit_max = (max_kv_len + split_keys - 1) / split_keys;
+    if ((size_t)M * nh * nsplit_max * hd > e->o_part_floats) return set_error("engine: attention workspace too small");
+
+    if (launch_add_norm(e->resid, nullptr, 0, 0, tokens, e->embed, e->layers[0].ln1, e->xnorm, M, h, c.rms_eps, s))
+        return -1;
+    for (int l = 0; l < c.n_layers; ++l) {
+        Layer& L = e->layers[l];
+        __nv_bfloat16* kc = e->kv_pool + (size_t)(2 * l) * e->kv_half;
+        __nv_bfloat16* vc = kc + e->kv_half;
+        if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, e->part, e->nqkv, e->nqkv, e->pdl, s)) return -1;
+        if (launch_qkv_rope(e->part, P->qkv.ksplit, (size_t)M * e->nqkv, L.bqkv, positions, token_slot, e->page_table,
+                            e->max_pages, e->inv_freq, e->q, kc, vc, M, nh, nkv, hd, c.page_size, s))
+            return -1;
+        AttnLaunch A;
+        A.q = e->q;
+        A.k_cache = kc;
+        A.v_cache = vc;
+        A.positions = positions;
+        A.token_slot = token_slot;
+        A.cu_q = cu_q;
+        A.seq_slot = seq_slot;
+        A.page_table = e->page_table;
+        A.out = e->attn;
+        A.o_part = e->o_part;
+        A.ml_part = e->ml_part;
+        A.M = M;
+        A.nseq = nseq;
+        A.max_qlen = max_qlen;
+        A.nh = nh;
+        A.nkv = nkv;
+        A.hd = hd;
+        A.page_size = c.page_size;
+        A.max_pages = e->max_pages;
+        A.split_keys = split_keys;
+        A.nsplit_max = nsplit_max;
+        A.impl = e->attn_impl;
+        if (launch_attention(A, s)) return -1;
+        if (gemm_launch(P->o, L.t_o, P->x_attn, e->part, h, h, e->pdl, s)) return -1;
+        int ns = P->o.ksplit;
+        if (tp) {
+            if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
+            ns = 1;
+        }
+        if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, L.ln2, e->xnorm, M, h, c.rms_eps, s))
+            return -1;
+        if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s)) return -1;
+        if (gemm_launch(P->down, L.t_down, P->x_act, e->part, h, h, e->pdl, s)) return -1;
+        ns = P->down.ksplit;
+        if (tp) {
+            if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
+            ns = 1;
+        }
+        const __nv_bfloat16* wn = (l + 1 < c.n_layers) ? e->layers[l + 1].ln1 : e->final_norm;
+        const bool last = l + 1 == c.n_layers;
+        if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, wn,
+                            (last && n_logit_rows == 0) ? nullptr : e->xnorm, M, h, c.rms_eps, s))
+            return -1;
+    }
+    if (n_logit_rows <= 0) return 0;
+    if (!logits_out) return set_error("engine: logits_out is NULL");
+    int rows = M;
+    const __nv_bfloat16* src = e->xnorm;
+    int key = M;
+    if (logit_rows) {
+        if (launch_gather_rows(e->xnorm, logit_rows, e->xsel, n_logit_rows, h, s)) return -1;
+        rows = n_logit_rows;
+        src = e->xsel;
+        key = -rows;
+    } else if (n_logit_rows != M) {
+        return set_error("engine: n_logit_rows must equal M when logit_rows is NULL");
+    }
+    auto it = e->lm_plans.find(key);
+    if (it == e->lm_plans.end()) {
+        std::pair<GemmPlan, CUtensorMap> v;
+        if (gemm_plan(&v.first, rows, c.vocab, h, GEMM_OUT_F32, 1, e->force_stages)) return -1;
+        if (make_tmap_bf16(&v.second, src, rows, h, h, v.first.MT)) return -1;
+        it = e->lm_plans.emplace(key, v).first;
+    }
+    return gemm_launch(it->second.first, e->t_lm, it->second.second, logits_out,
+                       logits_ld > 0 ? (int)logits_ld : c.vocab, c.vocab, e->pdl, s);
+}
+
+}  // namespace asd
+
+using namespace asd;
+
+extern "C" {
+
+asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
+    if (!cfg) {
+        set_error("asd_engine_create: NULL config");
+        return nullptr;
+    }
+    const asd_model_config& c = *cfg;
+    if (c.hidden <= 0 || c.hidden % 8 || c.hidden > 8192 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_kv_heads <= 0 ||
+        c.n_heads % c.n_kv_heads || (c.head_dim != 64 && c.head_dim != 128) || c.ffn <= 0 || c.ffn % 8 ||
+        c.vocab <= 0 || c.max_tokens <= 0 || c.page_size <= 0 || c.tp_size < 1) {
+        set_error("asd_engine_create: unsupported model shape");
+        return nullptr;
+    }
+    Engine* e = new Engine();
+    e->c = c;
+    e->nqkv = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
+    e->qdim = c.n_heads * c.head_dim;
+    e->ffp = (c.ffn + 63) / 64 * 64;
+    e->layers.resize(c.n_layers);
+    const size_t Mx = c.max_tokens;
+    e->part_floats = 16 * Mx * (size_t)std::max(e->nqkv, c.hidden);
+    e->o_part_floats = Mx * c.n_heads * (size_t)e->max_attn_splits * c.head_dim;
+    bool ok = true;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (ok && cudaMalloc(p, bytes) != cudaSuccess) {
+            ok = false;
+            set_error("asd_engine_create: cudaMalloc of %zu bytes failed", bytes);
+        }
+    };
+    alloc((void**)&e->resid, Mx * c.hidden * 4);
+    alloc((void**)&e->part, e->part_floats * 4);
+    alloc((void**)&e->o_part, e->o_part_floats * 4);
+    alloc((void**)&e->ml_part, Mx * c.n_heads * (size_t)e->max_attn_splits * 2 * 4);
+    alloc((void**)&e->xnorm, Mx * c.hidden * 2);
+    alloc((void**)&e->xsel, Mx * c.hidden * 2);
+    alloc((void**)&e->q, Mx * e->qdim * 2);
+    alloc((void**)&e->attn, Mx * e->qdim * 2);
+    alloc((void**)&e->act, Mx * (size_t)c.ffn * 2);
+    if (!ok) {
+        asd_engine_destroy(reinterpret_cast<asd_engine_t*>(e));
+        return nullptr;
+    }
+    return reinterpret_cast<asd_engine_t*>(e);
+}
+
+void asd_engine_destroy(asd_engine_t* h) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e) return;
+    void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->xnorm, e->xsel, e->q, e->attn, e->act};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    delete e;
+}
+
+int asd_engine_set_layer(asd_engine_t* h, int layer, const void* wqkv, const void* bqkv, const void* wo,
+                         const void* wgateup, const void* wdown, const void* ln1, const void* ln2) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || layer < 0 || layer >= e->c.n_layers) return set_error("asd_engine_set_layer: bad handle or layer");
+    if (!wqkv || !bqkv || !wo || !wgateup || !wdown || !ln1 || !ln2) return set_error("asd_engine_set_layer: NULL weight");
+    Layer& L = e->layers[layer];
+    L.wqkv = (const __nv_bfloat16*)wqkv;
+    L.bqkv = (const __nv_bfloat16*)bqkv;
+    L.wo = (const __nv_bfloat16*)wo;
+    L.wgu = (const __nv_bfloat16*)wgateup;
+    L.wdown = (const __nv_bfloat16*)wdown;
+    L.ln1 = (const __nv_bfloat16*)ln1;
+    L.ln2 = (const __nv_bfloat16*)ln2;
+    const int hdn = e->c.hidden;
+    if (make_tmap_bf16(&L.t_qkv, wqkv, e->nqkv, hdn, hdn, 128)) return -1;
+    if (make_tmap_bf16(&L.t_o, wo, hdn, e->qdim, e->qdim, 128)) return -1;
+    if (make_tmap_bf16(&L.t_gu, wgateup, 2 * e->ffp, hdn, hdn, 128)) return -1;
+    if (make_tmap_bf16(&L.t_down, wdown, hdn, e->c.ffn, e->c.ffn, 128)) return -1;
+    return 0;
+}
+
+int asd_engine_set_globals(asd_engine_t* h, const void* embed, const void* final_norm, const void* lm_head,
+                           const float* inv_freq) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !embed || !final_norm || !lm_head || !inv_freq) return set_error("asd_engine_set_globals: NULL argument");
+    e->embed = (const __nv_bfloat16*)embed;
+    e->final_norm = (const __nv_bfloat16*)final_norm;
+    e->lm_head = (const __nv_bfloat16*)lm_head;
+    e->inv_freq = inv_freq;
+    return make_tmap_bf16(&e->t_lm, lm_head, e->c.vocab, e->c.hidden, e->c.hidden, 128);
+}
+
+int asd_engine_set_kv(asd_engine_t* h, void* kv_pool, int num_pages, const int32_t* page_table, int max_seqs,
+                      int max_pages_per_seq) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !kv_pool || !page_table || num_pages <= 0) return set_error("asd_engine_set_kv: bad argument");
+    e->kv_pool = (__nv_bfloat16*)kv_pool;
+    e->num_pages = num_pages;
+    e->page_table = page_table;
+    e->max_seqs = max_seqs;
+    e->max_pages = max_pages_per_seq;
+    e->kv_half = (size_t)num_pages * e->c.n_kv_heads * e->c.page_size * e->c.head_dim;
+    return 0;
+}
+
+size_t asd_engine_kv_pool_bytes(const asd_model_config* c, int num_pages) {
+    return (size_t)2 * c->n_layers * num_pages * c->n_kv_heads * c->page_size * c->head_dim * 2;
+}
+
+int asd_engine_set_allreduce(asd_engine_t* h, void* comm, void* nccl_allreduce_fn) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e) return set_error("asd_engine_set_allreduce: NULL handle");
+    e->comm = comm;
+    e->allreduce = reinterpret_cast<allreduce_fn_t>(nccl_allreduce_fn);
+    return 0;
+}
+
+int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !name) return set_error("asd_engine_set_option: NULL argument");
+    if (!strcmp(name, "attn_impl")) e->attn_impl = value;
+    else if (!strcmp(name, "pdl")) e->pdl = value;
+    else if (!strcmp(name, "ksplit")) e->force_ksplit = value;
+    else if (!strcmp(name, "stages")) e->force_stages = value;
+    else return set_error("asd_engine_set_option: unknown option %s", name);
+    e->plans.clear();
+    e->lm_plans.clear();
+    return 0;
+}
+
+int asd_engine_forward(asd_engine_t* h, const int32_t* tokens, const int32_t* positions, const int32_t* token_slot,
+                       int M, const int32_t* cu_q, const int32_t* seq_slot, int nseq, int max_qlen, int max_kv_len,
+                       const int32_t* logit_rows, int n_logit_rows, float* logits_out, long long logits_ld,
+                       void* stream) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e) return set_error("asd_engine_forward: NULL handle");
+    if (!tokens || !positions || !token_slot || !cu_q || !seq_slot || nseq <= 0 || max_qlen <= 0 || max_kv_len <= 0)
+        return set_error("asd_engine_forward: bad argument");
+    return forward(e, tokens, positions, token_slot, M, cu_q, seq_slot, nseq, max_qlen, max_kv_len, logit_rows,
+                   n_logit_rows, logits_out, logits_ld, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

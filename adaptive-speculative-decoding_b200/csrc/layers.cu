@@ -1,0 +1,213 @@
+// Memory-bound glue kernels of the Qwen2 verify / draft forward.  Each one is fused with the
+// deterministic reduction of the GEMM's K-split fp32 slices so partial sums never make an extra
+// round trip:
+//   add_norm    : resid += sum_s part[s]  (or resid = embedding row);  x = RMSNorm(resid) * w  (bf16)
+//   qkv_rope    : qkv = sum_s part[s] + bias;  RoPE(q, k);  q -> bf16 buffer, k/v -> paged KV cache
+//   gather_rows : pick the rows whose logits are wanted
+// Model semantics follow HF Qwen2 (RMSNorm eps inside rsqrt, rotate_half RoPE, QKV bias), which is
+// what the reference's Stage wraps through vLLM (docs/guides/RESEARCH_PROTOCOL.md:233-304).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "asd_internal.h"
+#include "layers.h"
+#include "ptx.cuh"
+
+namespace asd {
+
+constexpr int kNormThreads = 256;
+constexpr int kNormMaxVec = 8;  // float4 per thread -> hidden <= 8192
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float t = 0.0f;
+    for (int w = 0; w < nw; ++w) t += scratch[w];  // fixed order: deterministic
+    return t;
+}
+
+// one CTA per token row
+__global__ void __launch_bounds__(kNormThreads) add_norm_kernel(float* __restrict__ resid, const float* __restrict__ part,
+                                                                 int nslices, size_t slice_stride,
+                                                                 const int* __restrict__ tokens,
+                                                                 const __nv_bfloat16* __restrict__ emb,
+                                                                 const __nv_bfloat16* __restrict__ w,
+                                                                 __nv_bfloat16* __restrict__ xnorm, int h, float eps) {
+    __shared__ float scratch[kNormThreads / 32];
+    grid_dep_launch();  // lets the next GEMM start streaming its weights (it waits before reading x)
+    const int m = blockIdx.x, nvec = h >> 2;
+    float4 v[kNormMaxVec];
+    float ss = 0.0f;
+    float4* rrow = reinterpret_cast<float4*>(resid + (size_t)m * h);
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+        const int c = threadIdx.x + i * kNormThreads;
+        if (c < nvec) {
+            float4 x;
+            if (tokens) {
+                const __nv_bfloat162* e =
+                    reinterpret_cast<const __nv_bfloat162*>(emb + (size_t)tokens[m] * h) + 2 * c;
+                const float2 a = __bfloat1622float2(e[0]), b = __bfloat1622float2(e[1]);
+                x = make_float4(a.x, a.y, b.x, b.y);
+            } else {
+                x = rrow[c];
+                for (int s = 0; s < nslices; ++s) {
+                    const float4 p = reinterpret_cast<const float4*>(part + s * slice_stride + (size_t)m * h)[c];
+                    x.x += p.x;
+                    x.y += p.y;
+                    x.z += p.z;
+                    x.w += p.w;
+                }
+            }
+            rrow[c] = x;
+            v[i] = x;
+            ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+    }
+    const float tot = block_sum(ss, scratch);
+    const float inv = rsqrtf(tot / (float)h + eps);
+    if (xnorm == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+        const int c = threadIdx.x + i * kNormThreads;
+        if (c < nvec) {
+            const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(w) + 2 * c;
+            const float2 w0 = __bfloat1622float2(wp[0]), w1 = __bfloat1622float2(wp[1]);
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(v[i].x * inv * w0.x, v[i].y * inv * w0.y);
+            __nv_bfloat162 o1 = __floats2bfloat162_rn(v[i].z * inv * w1.x, v[i].w * inv * w1.y);
+            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(xnorm + (size_t)m * h) + 2 * c;
+            op[0] = o0;
+            op[1] = o1;
+        }
+    }
+}
+
+int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_stride, const int* tokens,
+                    const __nv_bfloat16* emb, const __nv_bfloat16* w, __nv_bfloat16* xnorm, int M, int h, float eps,
+                    cudaStream_t stream) {
+    if (h % 4 || h > kNormThreads * kNormMaxVec * 4) return set_error("add_norm: hidden must be %%4 and <= 8192");
+    if (M <= 0) return 0;
+    add_norm_kernel<<<M, kNormThreads, 0, stream>>>(resid, part, nslices, slice_stride, tokens, emb, w, xnorm, h, eps);
+    ASD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+// reduce K-split slices into slice 0 (used before a tensor-parallel all-reduce)
+__global__ void reduce_slices_kernel(float* __restrict__ part, int nslices, size_t slice_stride, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 4 >= n) return;
+    float4 a = reinterpret_cast<float4*>(part)[i];
+    for (int s = 1; s < nslices; ++s) {
+        const float4 p = reinterpret_cast<const float4*>(part + s * slice_stride)[i];
+        a.x += p.x;
+        a.y += p.y;
+        a.z += p.z;
+        a.w += p.w;
+    }
+    reinterpret_cast<float4*>(part)[i] = a;
+}
+
+int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream) {
+    if (nslices <= 1 || n == 0) return 0;
+    const int threads = 256;
+    const size_t blocks = (n / 4 + threads - 1) / threads;
+    reduce_slices_kernel<<<(unsigned)blocks, threads, 0, stream>>>(part, nslices, slice_stride, n);
+    ASD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+// one CTA per token: bias, RoPE, q store, paged K/V append
+__global__ void __launch_bounds__(256) qkv_rope_kernel(const float* __restrict__ part, int nslices, size_t slice_stride,
+                                                        const __nv_bfloat16* __restrict__ bias,
+                                                        const int* __restrict__ positions,
+                                                        const int* __restrict__ token_slot,
+                                                        const int* __restrict__ page_table, int max_pages,
+                                                        const float* __restrict__ inv_freq,
+                                                        __nv_bfloat16* __restrict__ q_out,
+                                                        __nv_bfloat16* __restrict__ k_cache,
+                                                        __nv_bfloat16* __restrict__ v_cache, int nh, int nkv, int hd,
+                                                        int page_size) {
+    extern __shared__ float cs[];  // cos[hd/2], sin[hd/2]
+    grid_dep_launch();
+    const int m = blockIdx.x, half = hd >> 1;
+    const int pos = positions[m];
+    const int nqkv = (nh + 2 * nkv) * hd;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float s, c;
+        sincosf((float)pos * inv_freq[i], &s, &c);
+        cs[i] = c;
+        cs[half + i] = s;
+    }
+    __syncthreads();
+    const int slot = token_slot[m];
+    const int page = page_table[(size_t)slot * max_pages + pos / page_size];
+    const int in_page = pos % page_size;
+    const float* row = part + (size_t)m * nqkv;
+    auto val = [&](int c) {
+        float x = row[c];
+        for (int s = 1; s < nslices; ++s) x += row[s * slice_stride + c];
+        return x + __bfloat162float(bias[c]);
+    };
+    // rotary pairs of q and k heads
+    const int npairs = (nh + nkv) * half;
+    for (int t = threadIdx.x; t < npairs; t += blockDim.x) {
+        const int head = t / half, i = t - head * half;
+        const float x1 = val(head * hd + i), x2 = val(head * hd + i + half);
+        const float c = cs[i], s = cs[half + i];
+        const __nv_bfloat16 o1 = __float2bfloat16(x1 * c - x2 * s), o2 = __float2bfloat16(x2 * c + x1 * s);
+        if (head < nh) {
+            __nv_bfloat16* q = q_out + (size_t)m * nh * hd + head * hd;
+            q[i] = o1;
+            q[i + half] = o2;
+        } else {
+            const int g = head - nh;
+            __nv_bfloat16* k = k_cache + (((size_t)page * nkv + g) * page_size + in_page) * hd;
+            k[i] = o1;
+            k[i + half] = o2;
+        }
+    }
+    const int nv = nkv * hd;
+    for (int t = threadIdx.x; t < nv; t += blockDim.x) {
+        const int g = t / hd, d = t - g * hd;
+        v_cache[(((size_t)page * nkv + g) * page_size + in_page) * hd + d] = __float2bfloat16(val((nh + nkv) * hd + t));
+    }
+}
+
+int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const __nv_bfloat16* bias,
+                    const int* positions, const int* token_slot, const int* page_table, int max_pages,
+                    const float* inv_freq, __nv_bfloat16* q_out, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int M,
+                    int nh, int nkv, int hd, int page_size, cudaStream_t stream) {
+    if (M <= 0) return 0;
+    qkv_rope_kernel<<<M, 256, hd * sizeof(float), stream>>>(part, nslices, slice_stride, bias, positions, token_slot,
+                                                             page_table, max_pages, inv_freq, q_out, k_cache, v_cache,
+                                                             nh, nkv, hd, page_size);
+    ASD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ rows,
+                                   __nv_bfloat16* __restrict__ dst, int h) {
+    const int r = blockIdx.x, sr = rows[r];
+    const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)sr * h);
+    uint4* d = reinterpret_cast<uint4*>(dst + (size_t)r * h);
+    for (int i = threadIdx.x; i < h / 8; i += blockDim.x) d[i] = s[i];
+}
+
+int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16* dst, int n, int h,
+                       cudaStream_t stream) {
+    if (n <= 0) return 0;
+    gather_rows_kernel<<<n, 128, 0, stream>>>(src, rows, dst, h);
+    ASD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+}  // namespace asd

@@ -1,0 +1,36 @@
+// Host-side launchers of the non-GEMM kernels of the forward (layers.cu, attention.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace asd {
+
+int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_stride, const int* tokens,
+                    const __nv_bfloat16* emb, const __nv_bfloat16* w, __nv_bfloat16* xnorm, int M, int h, float eps,
+                    cudaStream_t stream);
+int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream);
+int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const __nv_bfloat16* bias,
+                    const int* positions, const int* token_slot, const int* page_table, int max_pages,
+                    const float* inv_freq, __nv_bfloat16* q_out, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int M,
+                    int nh, int nkv, int hd, int page_size, cudaStream_t stream);
+int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16* dst, int n, int h,
+                       cudaStream_t stream);
+
+struct AttnLaunch {
+    const __nv_bfloat16* q;
+    const __nv_bfloat16* k_cache;
+    const __nv_bfloat16* v_cache;
+    const int* positions;   // [M]
+    const int* token_slot;  // [M]
+    const int* cu_q;        // [nseq + 1]
+    const int* seq_slot;    // [nseq]
+    const int* page_table;  // [slots, max_pages]
+    __nv_bfloat16* out;     // [M, nh, hd]
+    float* o_part;
+    float* ml_part;
+    int M, nseq, max_qlen, nh, nkv, hd, page_size, max_pages, split_keys, nsplit_max, impl;
+};
+int launch_attention(const AttnLaunch& L, cudaStream_t stream);
+
+}  // namespace asd

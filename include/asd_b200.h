@@ -93,6 +93,71 @@ ASD_API int asd_linear_bf16(const void* x, const void* w, void* out, int M, int 
                     int stages, int* ksplit_used, void* stream);
 ASD_API int asd_linear_plan(int M, int N, int K, int out_mode, int* ksplit, int* stages, int* token_tile);
 
+/* ---------------------------------------------------------------------------------------------
+ * Model forward engine (Qwen2 family: RMSNorm, RoPE, GQA attention with QKV bias, SwiGLU MLP).
+ * Stands where the reference calls vllm.LLM(model, tensor_parallel_size, dtype="bfloat16",
+ * max_model_len=4096).generate(...)  (src/serving/real_model_pipeline.py:98-108,135;
+ * Stage.generate in docs/guides/RESEARCH_PROTOCOL.md:233-304).  One handle per (model, TP rank);
+ * calls on one handle must be serialised by the caller (the Python Stage holds a lock).
+ *
+ * Dimensions in asd_model_config are LOCAL to the tensor-parallel rank: n_heads, n_kv_heads and ffn
+ * are the global values divided by tp_size (column-parallel QKV / gate|up, row-parallel O / down);
+ * hidden and vocab are global (lm_head is replicated).
+ *
+ * Weight layouts (bf16, row-major, torch nn.Linear [out, in]):
+ *   wqkv [(n_heads + 2 n_kv_heads) * head_dim, hidden] = rows of q heads, then k heads, then v heads;
+ *   bqkv [(n_heads + 2 n_kv_heads) * head_dim];  wo [hidden, n_heads * head_dim];
+ *   wgateup [2 * ceil(ffn/64)*64, hidden]: per 128-row tile 64 gate rows then 64 up rows (zero padded);
+ *   wdown [hidden, ffn];  ln1, ln2, final_norm [hidden];  embed, lm_head [vocab, hidden];
+ *   inv_freq fp32 [head_dim / 2].
+ * KV pool (bf16, caller allocated, asd_engine_kv_pool_bytes):
+ *   [n_layers][2 (K, V)][num_pages][n_kv_heads][page_size][head_dim]; page_table i32
+ *   [max_seqs, max_pages_per_seq] maps (sequence slot, position / page_size) -> page.
+ */
+typedef struct asd_model_config {
+    int hidden, n_layers, n_heads, n_kv_heads, head_dim, ffn, vocab;
+    float rms_eps;
+    int max_tokens; /* largest M of one forward call */
+    int page_size;
+    int tp_rank, tp_size;
+} asd_model_config;
+typedef struct asd_engine asd_engine_t;
+
+ASD_API asd_engine_t* asd_engine_create(const asd_model_config* cfg); /* NULL on error */
+ASD_API void asd_engine_destroy(asd_engine_t* e);
+ASD_API int asd_engine_set_layer(asd_engine_t* e, int layer, const void* wqkv, const void* bqkv, const void* wo,
+                         const void* wgateup, const void* wdown, const void* ln1, const void* ln2);
+ASD_API int asd_engine_set_globals(asd_engine_t* e, const void* embed, const void* final_norm, const void* lm_head,
+                           const float* inv_freq);
+ASD_API size_t asd_engine_kv_pool_bytes(const asd_model_config* cfg, int num_pages);
+ASD_API int asd_engine_set_kv(asd_engine_t* e, void* kv_pool, int num_pages, const int32_t* page_table, int max_seqs,
+                      int max_pages_per_seq);
+/* comm: ncclComm_t; nccl_allreduce_fn: address of ncclAllReduce from the NCCL the process loaded.
+ * Called (fp32 sum, in place) after the O and down projections when tp_size > 1. */
+ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_allreduce_fn);
+/* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
+ * "ksplit", "stages" (0 = automatic) */
+ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
+/*
+ * One forward pass over M tokens (draft step: q_len 1; verify step: q_len k+1; prefill chunk).
+ *   tokens, positions, token_slot i32 [M]: token id, absolute position, sequence slot of each token;
+ *     the tokens of one sequence are contiguous and in increasing position;
+ *   cu_q i32 [nseq+1]: token range of each active sequence; seq_slot i32 [nseq]: its slot;
+ *   max_qlen: largest q_len (q_len * n_heads / n_kv_heads <= 128); max_kv_len: upper bound of
+ *     (last position + 1) over the sequences (sizes the flash-decoding split, may over-estimate);
+ *   K/V of the M tokens are written in place into the paged pool before attention: a rejected
+ *     speculative tail is rolled back by simply not advancing the caller's length (asd_kv_commit is
+ *     therefore a no-op in this design);
+ *   logit_rows i32 [n_logit_rows] selects rows (NULL = all M rows, n_logit_rows == M; 0 = no logits);
+ *   logits_out fp32 [n_logit_rows, vocab] with row stride logits_ld elements (0 = vocab).
+ * Asynchronous on `stream`; performs no allocation or synchronisation (CUDA-graph capturable after
+ * one warm-up call with the same M).
+ */
+ASD_API int asd_engine_forward(asd_engine_t* e, const int32_t* tokens, const int32_t* positions,
+                       const int32_t* token_slot, int M, const int32_t* cu_q, const int32_t* seq_slot, int nseq,
+                       int max_qlen, int max_kv_len, const int32_t* logit_rows, int n_logit_rows, float* logits_out,
+                       long long logits_ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,99 @@
+"""The CUDA forward engine (tcgen05 GEMMs + paged-KV attention) against the CPU fp32 oracle of the
+Qwen2 forward.  Tolerance from BASELINE.json north_star: logits max-abs <= 2e-2, argmax agreement
+>= 99.9 % (bf16 weights/activations on the device, fp32 everywhere in the oracle)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from asd_b200.models.qwen2 import Qwen2Config, random_hf_weights, tiny_config
+from oracle.model_oracle import qwen2_forward
+
+pytestmark = pytest.mark.gpu
+MAX_ABS, ARGMAX = 2e-2, 0.999
+
+
+def run_engine(cfg, w, ids, q_verify, attn_impl, chunk=0, max_tokens=64):
+    """prefill the first T - q_verify tokens (chunked), then ONE verify-style forward of q_verify tokens
+    per sequence; returns logits of the verify rows [B, q_verify, V] and of the last prefill row."""
+    from asd_b200.engine import QwenEngine
+    B, T = ids.shape
+    eng = QwenEngine(cfg, max_seqs=B + 1, max_seq_len=T + 16, max_tokens=max_tokens).load_hf_weights(w)
+    eng.set_option("attn_impl", attn_impl)
+    slots = torch.arange(1, B + 1, dtype=torch.int32, device="cuda")      # slot 0 deliberately unused
+    P = T - q_verify
+    idc = ids.cuda().to(torch.int32)
+    last = eng.prefill(idc[:, :P], slots, chunk=chunk)
+    start = torch.full((B,), P, dtype=torch.int32, device="cuda")
+    ver = eng.forward_uniform(idc[:, P:].contiguous(), start, slots, T)
+    torch.cuda.synchronize()
+    out = ver.view(B, q_verify, -1).cpu(), last.cpu()
+    eng.close()
+    return out
+
+
+def check(got, ref):
+    err = (got - ref).abs().max().item()
+    agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    assert err <= MAX_ABS, err
+    assert agree >= ARGMAX, agree
+
+
+@pytest.mark.parametrize("attn_impl", [0, 1])
+@pytest.mark.parametrize("name,cfg,B,T,q", [
+    ("tiny-hd64", tiny_config(), 3, 37, 5),
+    ("g5-hd128", Qwen2Config(512, 2, 10, 2, 1024, 4096, head_dim=128, name="g5"), 4, 150, 6),
+    ("g7-hd128", Qwen2Config(896, 2, 7, 1, 1280, 2048, head_dim=128, name="g7"), 2, 70, 1),
+    ("g8-hd128-long", Qwen2Config(1024, 1, 8, 1, 512, 1024, head_dim=128, name="g8"), 2, 700, 9),
+])
+def test_engine_logits_vs_oracle(name, cfg, B, T, q, attn_impl):
+    w = random_hf_weights(cfg, seed=11)
+    ids = torch.randint(0, cfg.vocab_size, (B, T), generator=torch.Generator().manual_seed(5))
+    ref = qwen2_forward(w, cfg, ids)
+    ver, last = run_engine(cfg, w, ids, q, attn_impl)
+    check(ver, ref[:, T - q:])
+    check(last, ref[:, T - q - 1])
+
+
+def test_engine_hf_golden_weights():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qwen2_tiny_golden.npz"))
+    w = {k[3:]: torch.from_numpy(z[k]).view(torch.bfloat16) for k in z.files if k.startswith("w::")}
+    ids = torch.from_numpy(z["input_ids"]).long()
+    ref = torch.from_numpy(z["logits"])       # HF Qwen2ForCausalLM fp32 logits
+    ver, last = run_engine(tiny_config(), w, ids, 4, 1, chunk=7)
+    check(ver, ref[:, -4:])
+    check(last, ref[:, -5])
+
+
+def test_engine_qwen05b_shapes_two_layers():
+    """real Qwen2.5-0.5B shapes (V = 151936, tied embeddings) with 2 layers: config-1-like verify, k = 4"""
+    from dataclasses import replace
+    from asd_b200.models.qwen2 import QWEN25
+    cfg = replace(QWEN25["0.5b"], num_hidden_layers=2)
+    w = random_hf_weights(cfg, seed=0)
+    ids = torch.randint(0, cfg.vocab_size, (1, 69), generator=torch.Generator().manual_seed(1234))
+    ref = qwen2_forward(w, cfg, ids)
+    ver, last = run_engine(cfg, w, ids, 5, 1)
+    check(ver, ref[:, -5:])
+
+
+def test_rollback_overwrites_rejected_tail():
+    """speculative K/V written past the accepted length are simply overwritten: re-running a verify at
+    the same positions with different tokens gives the same logits as a fresh engine."""
+    cfg = tiny_config()
+    w = random_hf_weights(cfg, seed=2)
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(0, cfg.vocab_size, (2, 30), generator=g)
+    junk = ids.clone()
+    junk[:, 24:] = torch.randint(0, cfg.vocab_size, (2, 6), generator=g)
+    from asd_b200.engine import QwenEngine
+    eng = QwenEngine(cfg, max_seqs=2, max_seq_len=64, max_tokens=32).load_hf_weights(w)
+    slots = torch.arange(2, dtype=torch.int32, device="cuda")
+    eng.prefill(junk[:, :24].cuda().to(torch.int32), slots)
+    start = torch.full((2,), 24, dtype=torch.int32, device="cuda")
+    eng.forward_uniform(junk[:, 24:].cuda().to(torch.int32), start, slots, 30)          # rejected speculation
+    got = eng.forward_uniform(ids[:, 24:].cuda().to(torch.int32), start, slots, 30).view(2, 6, -1).cpu()
+    ref = qwen2_forward(w, cfg, ids)
+    check(got, ref[:, 24:])
+    eng.close()
