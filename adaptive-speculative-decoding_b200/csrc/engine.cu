@@ -57,7 +57,36 @@ struct Engine {
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
+    // profiling (option "profile"): CUDA-event pairs around every launch, by kernel class
+    int profile = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::pair<int, int>> ev_used;  // (class, pool index)
+    size_t ev_next = 0;
 };
+
+enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_GLUE = 2, PROF_COMM = 3, PROF_LMHEAD = 4, PROF_NCLASS = 5 };
+
+struct ProfScope {
+    Engine* e;
+    cudaStream_t s;
+    int idx = -1;
+    ProfScope(Engine* e_, int cls, cudaStream_t s_) : e(e_), s(s_) {
+        if (!e->profile) return;
+        if (e->ev_next == e->ev_pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            e->ev_pool.emplace_back(a, b);
+        }
+        idx = (int)e->ev_next++;
+        e->ev_used.emplace_back(cls, idx);
+        cudaEventRecord(e->ev_pool[idx].first, s);
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(e->ev_pool[idx].second, s);
+    }
+};
+#define PROF(cls) ProfScope _prof_scope(e, cls, s)
 
 static int ensure_plans(Engine* e, int M, Plans** out) {
     auto it = e->plans.find(M);
@@ -115,16 +144,25 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     const int nsplit_max = (max_kv_len + split_keys - 1) / split_keys;
     if ((size_t)M * nh * nsplit_max * hd > e->o_part_floats) return set_error("engine: attention workspace too small");
 
-    if (launch_add_norm(e->resid, nullptr, 0, 0, tokens, e->embed, e->layers[0].ln1, e->xnorm, M, h, c.rms_eps, s))
-        return -1;
+    {
+        PROF(PROF_GLUE);
+        if (launch_add_norm(e->resid, nullptr, 0, 0, tokens, e->embed, e->layers[0].ln1, e->xnorm, M, h, c.rms_eps, s))
+            return -1;
+    }
     for (int l = 0; l < c.n_layers; ++l) {
         Layer& L = e->layers[l];
         __nv_bfloat16* kc = e->kv_pool + (size_t)(2 * l) * e->kv_half;
         __nv_bfloat16* vc = kc + e->kv_half;
-        if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, e->part, e->nqkv, e->nqkv, e->pdl, s)) return -1;
+        {
+            PROF(PROF_GEMM);
+            if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, e->part, e->nqkv, e->nqkv, e->pdl, s)) return -1;
+        }
+        {
+        PROF(PROF_GLUE);
         if (launch_qkv_rope(e->part, P->qkv.ksplit, (size_t)M * e->nqkv, L.bqkv, positions, token_slot, e->page_table,
                             e->max_pages, e->inv_freq, e->q, kc, vc, M, nh, nkv, hd, c.page_size, s))
             return -1;
+        }
         AttnLaunch A;
         A.q = e->q;
         A.k_cache = kc;
@@ -148,22 +186,41 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         A.split_keys = split_keys;
         A.nsplit_max = nsplit_max;
         A.impl = e->attn_impl;
-        if (launch_attention(A, s)) return -1;
-        if (gemm_launch(P->o, L.t_o, P->x_attn, e->part, h, h, e->pdl, s)) return -1;
+        {
+            PROF(PROF_ATTN);
+            if (launch_attention(A, s)) return -1;
+        }
+        {
+            PROF(PROF_GEMM);
+            if (gemm_launch(P->o, L.t_o, P->x_attn, e->part, h, h, e->pdl, s)) return -1;
+        }
         int ns = P->o.ksplit;
         if (tp) {
+            PROF(PROF_COMM);
             if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
             ns = 1;
         }
-        if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, L.ln2, e->xnorm, M, h, c.rms_eps, s))
-            return -1;
-        if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s)) return -1;
-        if (gemm_launch(P->down, L.t_down, P->x_act, e->part, h, h, e->pdl, s)) return -1;
+        {
+            PROF(PROF_GLUE);
+            if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, L.ln2, e->xnorm, M, h,
+                                c.rms_eps, s))
+                return -1;
+        }
+        {
+            PROF(PROF_GEMM);
+            if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s)) return -1;
+        }
+        {
+            PROF(PROF_GEMM);
+            if (gemm_launch(P->down, L.t_down, P->x_act, e->part, h, h, e->pdl, s)) return -1;
+        }
         ns = P->down.ksplit;
         if (tp) {
+            PROF(PROF_COMM);
             if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
             ns = 1;
         }
+        PROF(PROF_GLUE);
         const __nv_bfloat16* wn = (l + 1 < c.n_layers) ? e->layers[l + 1].ln1 : e->final_norm;
         const bool last = l + 1 == c.n_layers;
         if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, wn,
@@ -190,6 +247,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         if (make_tmap_bf16(&v.second, src, rows, h, h, v.first.MT)) return -1;
         it = e->lm_plans.emplace(key, v).first;
     }
+    PROF(PROF_LMHEAD);
     return gemm_launch(it->second.first, e->t_lm, it->second.second, logits_out,
                        logits_ld > 0 ? (int)logits_ld : c.vocab, c.vocab, e->pdl, s);
 }
@@ -317,9 +375,34 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "pdl")) e->pdl = value;
     else if (!strcmp(name, "ksplit")) e->force_ksplit = value;
     else if (!strcmp(name, "stages")) e->force_stages = value;
+    else if (!strcmp(name, "profile")) {
+        e->profile = value;
+        e->ev_used.clear();
+        e->ev_next = 0;
+        return 0;
+    }
     else return set_error("asd_engine_set_option: unknown option %s", name);
     e->plans.clear();
     e->lm_plans.clear();
+    return 0;
+}
+
+int asd_engine_profile_read(asd_engine_t* h, float* ms_by_class, int* launches_by_class, int nclass) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !ms_by_class || nclass < PROF_NCLASS) return set_error("asd_engine_profile_read: bad argument");
+    ASD_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < nclass; ++i) {
+        ms_by_class[i] = 0.0f;
+        if (launches_by_class) launches_by_class[i] = 0;
+    }
+    for (auto& u : e->ev_used) {
+        float ms = 0.0f;
+        ASD_CUDA(cudaEventElapsedTime(&ms, e->ev_pool[u.second].first, e->ev_pool[u.second].second));
+        ms_by_class[u.first] += ms;
+        if (launches_by_class) launches_by_class[u.first] += 1;
+    }
+    e->ev_used.clear();
+    e->ev_next = 0;
     return 0;
 }
 

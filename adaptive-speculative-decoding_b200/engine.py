@@ -101,6 +101,15 @@ class QwenEngine:
     def set_option(self, name: str, value: int):
         check(lib().asd_engine_set_option(self.h, name.encode(), int(value)), "asd_engine_set_option")
 
+    PROFILE_CLASSES = ("gemm", "attention", "glue", "allreduce", "lm_head")
+
+    def profile_read(self):
+        """(ms, launches) per kernel class since the last read; needs set_option('profile', 1)."""
+        ms = (ctypes.c_float * 5)()
+        n = (ctypes.c_int * 5)()
+        check(lib().asd_engine_profile_read(self.h, ms, n, 5), "asd_engine_profile_read")
+        return {c: (ms[i], n[i]) for i, c in enumerate(self.PROFILE_CLASSES)}
+
     def set_allreduce(self, comm_ptr: int, fn_ptr: int):
         check(lib().asd_engine_set_allreduce(self.h, ctypes.c_void_p(comm_ptr), ctypes.c_void_p(fn_ptr)),
               "asd_engine_set_allreduce")
@@ -242,6 +251,21 @@ class SpecDecoder:
         self.pos = self.pos + out["accepted_len"] + 1
         self.kv_bound = bound
         return out
+
+    def step_host(self, host_state: torch.Tensor, host_tokens: torch.Tensor, host_accepted: torch.Tensor):
+        """Same step driven from HOST (pinned) buffers, the way a non-torch integrator would call it:
+        host_state int32 [3, B] = (last_tok, prev_tok, pos) is copied to the device, the step runs, then
+        the emitted tokens [B, k+1], accepted lengths [B] and the next state (in place) are copied back;
+        returns after the copy-out has completed."""
+        dev_state = host_state.to(self.device, non_blocking=True)
+        self.last_tok, self.prev_tok, self.pos = (dev_state[0].contiguous(), dev_state[1].contiguous(),
+                                                  dev_state[2].contiguous())
+        out = self.step()
+        host_tokens.copy_(out["out_tokens"], non_blocking=True)
+        host_accepted.copy_(out["accepted_len"], non_blocking=True)
+        host_state.copy_(torch.stack([self.last_tok, self.prev_tok, self.pos]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_tokens, host_accepted
 
     def _sample_rows_strided(self, i: int) -> torch.Tensor:
         # the fused sampler wants contiguous rows: draft step i wrote rows with stride k*V

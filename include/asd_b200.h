@@ -138,6 +138,11 @@ ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_all
 /* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
  * "ksplit", "stages" (0 = automatic) */
 ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
+/* With option "profile" = 1 every launch is bracketed by CUDA events on the launching stream;
+ * this call synchronises and returns the summed milliseconds and launch counts by kernel class
+ * {0 weight-streaming GEMMs, 1 attention, 2 glue (norm/rope/gather), 3 TP all-reduce, 4 lm_head GEMM}
+ * since the previous read (bench.py's roofline numbers come from here). nclass >= 5. */
+ASD_API int asd_engine_profile_read(asd_engine_t* e, float* ms_by_class, int* launches_by_class, int nclass);
 /*
  * One forward pass over M tokens (draft step: q_len 1; verify step: q_len k+1; prefill chunk).
  *   tokens, positions, token_slot i32 [M]: token id, absolute position, sequence slot of each token;

@@ -97,3 +97,56 @@ def test_rollback_overwrites_rejected_tail():
     ref = qwen2_forward(w, cfg, ids)
     check(got, ref[:, 24:])
     eng.close()
+
+
+def test_spec_decode_greedy_equals_plain_greedy():
+    """speculative decoding invariant: with greedy verification the emitted sequence is exactly the
+    target model's own greedy continuation, whatever the draft proposes."""
+    from asd_b200.engine import QwenEngine, SpecDecoder
+    tcfg = tiny_config()
+    dcfg = tiny_config(num_hidden_layers=1)
+    wt, wd = random_hf_weights(tcfg, seed=21, std=0.08), random_hf_weights(dcfg, seed=22, std=0.08)
+    B, P, NEW, k = 3, 12, 40, 4
+    prompts = torch.randint(0, tcfg.vocab_size, (B, P), generator=torch.Generator().manual_seed(3))
+
+    def generate(use_draft):
+        t = QwenEngine(tcfg, max_seqs=B, max_seq_len=128, max_tokens=64).load_hf_weights(wt)
+        d = QwenEngine(dcfg, max_seqs=B, max_seq_len=128, max_tokens=64).load_hf_weights(wd) if use_draft else None
+        dec = SpecDecoder(t, d, B, k, temperature=0.0)
+        first = dec.prefill(prompts).cpu()
+        seqs = [[int(first[b])] for b in range(B)]
+        acc_total = 0
+        while min(len(s) for s in seqs) < NEW:
+            out = dec.step()
+            toks, n = out["out_tokens"].cpu(), out["accepted_len"].cpu()
+            acc_total += int(n.sum())
+            for b in range(B):
+                seqs[b] += [int(x) for x in toks[b, :n[b] + 1]]
+        return [s[:NEW] for s in seqs], acc_total
+
+    plain, _ = generate(False)
+    spec, acc = generate(True)
+    assert spec == plain
+    # the oracle agrees on the first tokens (fp32 CPU vs bf16 device: compare the prefix before any near-tie)
+    ref = qwen2_forward(wt, tcfg, prompts)
+    assert [s[0] for s in plain] == ref[:, -1].argmax(-1).tolist()
+
+
+def test_spec_decode_sampling_runs_and_self_draft_accepts_everything():
+    """draft == target (same weights): p == q, so every draft token is accepted at any temperature."""
+    from asd_b200.engine import QwenEngine, SpecDecoder
+    cfg = tiny_config()
+    w = random_hf_weights(cfg, seed=5, std=0.08)
+    B, k = 2, 3
+    t = QwenEngine(cfg, max_seqs=B, max_seq_len=128, max_tokens=64).load_hf_weights(w)
+    d = QwenEngine(cfg, max_seqs=B, max_seq_len=128, max_tokens=64).load_hf_weights(w)
+    dec = SpecDecoder(t, d, B, k, temperature=0.7)
+    dec.prefill(torch.randint(0, cfg.vocab_size, (B, 9), generator=torch.Generator().manual_seed(1)))
+    tot = 0
+    for _ in range(6):
+        out = dec.step()
+        tot += int(out["accepted_len"].sum())
+        assert (out["out_tokens"][:, 0] >= 0).all()
+    # draft rows are computed at M = B (or 2B), target rows at M = B*(k+1): identical weights give the
+    # same logits up to fp32 summation order, so p/q = 1 +- 1e-5 and u <= p/q except for u within 1e-5 of 1
+    assert tot >= 6 * B * k - 1
