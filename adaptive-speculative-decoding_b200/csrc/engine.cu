@@ -54,7 +54,7 @@ struct Engine {
     std::unordered_map<int, Plans> plans;
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     // options
-    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16;
+    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // profiling (option "profile"): CUDA-event pairs around every launch, by kernel class
@@ -96,10 +96,10 @@ static int ensure_plans(Engine* e, int M, Plans** out) {
     }
     Plans p;
     const int h = e->c.hidden;
-    if (gemm_plan(&p.qkv, M, e->nqkv, h, GEMM_OUT_F32, e->force_ksplit, e->force_stages)) return -1;
-    if (gemm_plan(&p.o, M, h, e->qdim, GEMM_OUT_F32, e->force_ksplit, e->force_stages)) return -1;
-    if (gemm_plan(&p.gu, M, 2 * e->ffp, h, GEMM_OUT_SWIGLU, 0, e->force_stages)) return -1;
-    if (gemm_plan(&p.down, M, h, e->c.ffn, GEMM_OUT_F32, e->force_ksplit, e->force_stages)) return -1;
+    if (gemm_plan(&p.qkv, M, e->nqkv, h, GEMM_OUT_F32, e->force_ksplit, e->force_stages, e->reduce)) return -1;
+    if (gemm_plan(&p.o, M, h, e->qdim, GEMM_OUT_F32, e->force_ksplit, e->force_stages, e->reduce)) return -1;
+    if (gemm_plan(&p.gu, M, 2 * e->ffp, h, GEMM_OUT_SWIGLU, 0, e->force_stages, 0)) return -1;
+    if (gemm_plan(&p.down, M, h, e->c.ffn, GEMM_OUT_F32, e->force_ksplit, e->force_stages, e->reduce)) return -1;
     const size_t need = (size_t)M * std::max(std::max((size_t)p.qkv.ksplit * e->nqkv, (size_t)p.o.ksplit * h),
                                              (size_t)p.down.ksplit * h);
     if (need > e->part_floats) return set_error("engine: split-K workspace too small for M = %d", M);
@@ -159,7 +159,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         }
         {
         PROF(PROF_GLUE);
-        if (launch_qkv_rope(e->part, P->qkv.ksplit, (size_t)M * e->nqkv, L.bqkv, positions, token_slot, e->page_table,
+        if (launch_qkv_rope(e->part, P->qkv.reduce ? 1 : P->qkv.ksplit, (size_t)M * e->nqkv, L.bqkv, positions, token_slot, e->page_table,
                             e->max_pages, e->inv_freq, e->q, kc, vc, M, nh, nkv, hd, c.page_size, s))
             return -1;
         }
@@ -190,11 +190,14 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             PROF(PROF_ATTN);
             if (launch_attention(A, s)) return -1;
         }
+        // fused residual add: with the in-cluster reduction the GEMM accumulates straight into resid
+        const bool fuse_o = !tp && (P->o.reduce || P->o.ksplit == 1);
         {
             PROF(PROF_GEMM);
-            if (gemm_launch(P->o, L.t_o, P->x_attn, e->part, h, h, e->pdl, s)) return -1;
+            if (gemm_launch(P->o, L.t_o, P->x_attn, fuse_o ? (void*)e->resid : (void*)e->part, h, h, e->pdl, s, fuse_o))
+                return -1;
         }
-        int ns = P->o.ksplit;
+        int ns = fuse_o ? 0 : (P->o.reduce ? 1 : P->o.ksplit);
         if (tp) {
             PROF(PROF_COMM);
             if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
@@ -210,11 +213,14 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             PROF(PROF_GEMM);
             if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s)) return -1;
         }
+        const bool fuse_d = !tp && (P->down.reduce || P->down.ksplit == 1);
         {
             PROF(PROF_GEMM);
-            if (gemm_launch(P->down, L.t_down, P->x_act, e->part, h, h, e->pdl, s)) return -1;
+            if (gemm_launch(P->down, L.t_down, P->x_act, fuse_d ? (void*)e->resid : (void*)e->part, h, h, e->pdl, s,
+                            fuse_d))
+                return -1;
         }
-        ns = P->down.ksplit;
+        ns = fuse_d ? 0 : (P->down.reduce ? 1 : P->down.ksplit);
         if (tp) {
             PROF(PROF_COMM);
             if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
@@ -243,7 +249,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     auto it = e->lm_plans.find(key);
     if (it == e->lm_plans.end()) {
         std::pair<GemmPlan, CUtensorMap> v;
-        if (gemm_plan(&v.first, rows, c.vocab, h, GEMM_OUT_F32, 1, e->force_stages)) return -1;
+        if (gemm_plan(&v.first, rows, c.vocab, h, GEMM_OUT_F32, 1, e->force_stages, 0)) return -1;
         if (make_tmap_bf16(&v.second, src, rows, h, h, v.first.MT)) return -1;
         it = e->lm_plans.emplace(key, v).first;
     }
@@ -375,6 +381,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "pdl")) e->pdl = value;
     else if (!strcmp(name, "ksplit")) e->force_ksplit = value;
     else if (!strcmp(name, "stages")) e->force_stages = value;
+    else if (!strcmp(name, "reduce")) e->reduce = value;
     else if (!strcmp(name, "profile")) {
         e->profile = value;
         e->ev_used.clear();

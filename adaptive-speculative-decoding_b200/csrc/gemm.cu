@@ -45,6 +45,8 @@ struct GemmArgs {
     int n_valid;        // rows of the output that exist (SwiGLU: ff; else N)
     void* out;
     uint32_t tmem_cols;
+    int reduce;         // 1: the K splits of a tile form a cluster and reduce through DSMEM
+    int accumulate;     // fp32 output is added to what is already there (fused residual add)
 };
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
@@ -150,7 +152,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         tc_fence_after();
         grid_dep_launch();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (a.mode == GEMM_OUT_SWIGLU) {
+        if (a.reduce) {
+            // handled below by the whole cluster
+        } else if (a.mode == GEMM_OUT_SWIGLU) {
             // rows 0..63 = gate, 64..127 = up of ff index tile_n*64 + (row & 63)
             const int et = threadIdx.x - 64;      // 0..127 among epilogue threads
             __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
@@ -204,13 +208,65 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int m = m0 + c0 + i;
-                            if (c0 + i < a.MT && m < a.M) out[(size_t)m * a.ldo + n] = __uint_as_float(r[i]);
+                            if (c0 + i < a.MT && m < a.M) {
+                                float* o = out + (size_t)m * a.ldo + n;
+                                *o = a.accumulate ? *o + __uint_as_float(r[i]) : __uint_as_float(r[i]);
+                            }
                         }
                     }
                 }
             }
         }
         tc_fence_before();
+    }
+    if (a.reduce) {
+        // ---- split-K reduction inside the cluster (deterministic, no HBM round trip of partials):
+        // CTA r of the cluster owns accumulator rows [r*rows_per, (r+1)*rows_per); every CTA sends
+        // those rows of its partial tile into the owner's (now idle) smem ring through DSMEM, the
+        // owner adds the ksplit contributions in rank order and writes the final values once.
+        const int ks = a.ksplit, rows_per = (kTileN + ks - 1) / ks;
+        const uint32_t my_rank = cluster_ctarank();
+        if (warp < 2) mbar_wait(tmem_full, 0);  // own MMAs done => nothing reads or fills the ring any more
+        tc_fence_after();
+        fence_proxy_async_smem();
+        cluster_sync();
+        // receive layout in the owner: recv[src][col][lrow] (lrow contiguous) so that the 32 lanes of a
+        // warp (32 consecutive accumulator rows) write contiguous 64-128 byte runs through DSMEM
+        if (warp >= 2) {
+            const int q = warp & 3, row = q * 32 + lane;
+            const int owner = row / rows_per, lrow = row - owner * rows_per;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t dst = mapa(smem_u32(smem) + (uint32_t)((int)my_rank * a.MT * rows_per + lrow) * 4u,
+                                      (uint32_t)owner);
+            for (int c0 = 0; c0 < a.MT; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < a.MT) st_cluster_u32(dst + (uint32_t)((c0 + i) * rows_per) * 4u, r[i]);
+            }
+            tc_fence_before();
+        }
+        cluster_sync();
+        if (warp >= 2) {
+            const int et = threadIdx.x - 64;
+            const int first = (int)my_rank * rows_per;
+            const int nrows = min(rows_per, kTileN - first);
+            const float* recv = reinterpret_cast<const float*>(smem);
+            float* out = static_cast<float*>(a.out);
+            const int m0 = tile_m * a.MT;
+            for (int idx = et; idx < rows_per * a.MT; idx += 128) {
+                const int col = idx / rows_per, lrow = idx - col * rows_per;
+                float acc = recv[idx];
+                for (int src = 1; src < ks; ++src) acc += recv[src * a.MT * rows_per + idx];
+                const int n = tile_n * kTileN + first + lrow, m = m0 + col;
+                if (lrow < nrows && m < a.M && n < a.n_valid) {
+                    float* o = out + (size_t)m * a.ldo + n;
+                    *o = a.accumulate ? *o + acc : acc;
+                }
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -275,8 +331,9 @@ int gemm_token_tile(int M) {
 }
 
 // Choose the split so that all CTAs fit in one co-resident wave and there are enough bytes in flight.
-int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages) {
+int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages, int reduce) {
     if (device_props()) return -1;
+    pl->reduce = (reduce && mode == GEMM_OUT_F32) ? 1 : 0;
     if (M <= 0 || N <= 0 || K <= 0 || (K & 7)) return set_error("gemm: need M, N, K > 0 and K %% 8 == 0");
     pl->M = M;
     pl->N = N;
@@ -298,20 +355,33 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     const int tiles = pl->n_tiles * pl->m_tiles;
     int ksplit = 1;
     if (mode != GEMM_OUT_SWIGLU && mode != GEMM_OUT_BF16) {
-        // largest split that keeps every CTA resident, each with >= 4 k-blocks of work
+        // largest split that keeps every CTA resident, each with >= 4 k-blocks of work; with the
+        // in-cluster reduction the split is bounded by the portable cluster size (8)
         ksplit = slots / tiles;
         if (ksplit < 1) ksplit = 1;
         const int max_by_k = pl->kblocks / 4 > 0 ? pl->kblocks / 4 : 1;
         if (ksplit > max_by_k) ksplit = max_by_k;
-        if (ksplit > 16) ksplit = 16;
+        if (ksplit > (pl->reduce ? 8 : 16)) ksplit = pl->reduce ? 8 : 16;
+        if (pl->reduce) {  // cluster sizes that tile the GPCs evenly: 1, 2, 4, 8
+            int p2 = 1;
+            while (p2 * 2 <= ksplit) p2 *= 2;
+            ksplit = p2;
+        }
     }
     if (force_ksplit > 0) ksplit = force_ksplit;
     if (force_stages > 0) stages = force_stages;
+    if (pl->reduce && ksplit > 1) {
+        if (ksplit > 8) return set_error("gemm: cluster reduction supports ksplit <= 8");
+        const int rows_per = (kTileN + ksplit - 1) / ksplit;
+        const int recv = ksplit * rows_per * pl->MT * 4;
+        while (stages * stage_bytes < recv) ++stages;   // the receive buffer overlays the tile ring
+    }
     if ((mode == GEMM_OUT_SWIGLU || mode == GEMM_OUT_BF16) && ksplit != 1)
         return set_error("gemm: bf16 / SwiGLU epilogues need ksplit == 1");
     if (ksplit > pl->kblocks) ksplit = pl->kblocks;
     pl->ksplit = ksplit;
     pl->stages = stages;
+    if (ksplit == 1) pl->reduce = 0;
     pl->smem_bytes = fixed + stages * stage_bytes;
     if (pl->smem_bytes > g_smem_optin) return set_error("gemm: tile does not fit in shared memory");
     uint32_t cols = 32;
@@ -321,7 +391,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
 }
 
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
-                int n_valid, bool pdl, cudaStream_t stream) {
+                int n_valid, bool pdl, cudaStream_t stream, bool accumulate) {
     if (!g_gemm_attr_set) {
         if (device_props()) return -1;
         ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
@@ -340,18 +410,31 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.n_valid = n_valid;
     a.out = out;
     a.tmem_cols = pl.tmem_cols;
+    a.reduce = pl.reduce;
+    a.accumulate = accumulate ? 1 : 0;
+    if (accumulate && pl.mode != GEMM_OUT_F32) return set_error("gemm: accumulate needs the fp32 epilogue");
+    if (accumulate && pl.ksplit > 1 && !pl.reduce) return set_error("gemm: accumulate needs the cluster reduction");
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     cfg.gridDim = dim3(pl.n_tiles, pl.ksplit, pl.m_tiles);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = stream;
+    int na = 0;
     if (pdl) {
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
     }
+    if (pl.reduce) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = pl.ksplit;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
     ASD_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel, tmap_w, tmap_x, a));
     count_launch(1);
     return 0;
@@ -365,19 +448,22 @@ extern "C" int asd_linear_bf16(const void* x, const void* w, void* out, int M, i
                                int ksplit, int stages, int* ksplit_used, void* stream) {
     using namespace asd;
     GemmPlan pl;
-    if (out_mode < 0 || out_mode > 2) return set_error("asd_linear_bf16: bad out_mode");
-    if (gemm_plan(&pl, M, N, K, out_mode, ksplit, stages)) return -1;
+    if (out_mode < 0 || out_mode > 3) return set_error("asd_linear_bf16: bad out_mode");
+    const int reduce = out_mode == 3;
+    if (reduce) out_mode = GEMM_OUT_F32;
+    if (gemm_plan(&pl, M, N, K, out_mode, ksplit, stages, reduce)) return -1;
     CUtensorMap tw, tx;
     if (make_tmap_bf16(&tw, w, N, K, K, 128)) return -1;
     if (make_tmap_bf16(&tx, x, M, K, K, pl.MT)) return -1;
     if (ksplit_used) *ksplit_used = pl.ksplit;
     const int ldo = out_mode == GEMM_OUT_SWIGLU ? N / 2 : N;
-    return gemm_launch(pl, tw, tx, out, ldo, ldo, false, static_cast<cudaStream_t>(stream));
+    return gemm_launch(pl, tw, tx, out, ldo, ldo, false, static_cast<cudaStream_t>(stream), false);
 }
 extern "C" int asd_linear_plan(int M, int N, int K, int out_mode, int* ksplit, int* stages, int* token_tile) {
     using namespace asd;
     GemmPlan pl;
-    if (gemm_plan(&pl, M, N, K, out_mode, 0, 0)) return -1;
+    if (out_mode < 0 || out_mode > 3) return set_error("asd_linear_plan: bad out_mode");
+    if (gemm_plan(&pl, M, N, K, out_mode == 3 ? GEMM_OUT_F32 : out_mode, 0, 0, out_mode == 3)) return -1;
     if (ksplit) *ksplit = pl.ksplit;
     if (stages) *stages = pl.stages;
     if (token_tile) *token_tile = pl.MT;

@@ -10,17 +10,19 @@ enum GemmOut { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_SWIGLU = 2 };
 
 struct GemmPlan {
     int M, N, K, mode;
-    int MT, m_tiles, n_tiles, kblocks, ksplit, stages, smem_bytes;
+    int MT, m_tiles, n_tiles, kblocks, ksplit, stages, smem_bytes, reduce;
     uint32_t tmem_cols;
 };
 
 int gemm_token_tile(int M);
-int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages);
+// reduce = 1: the K splits of a tile form a thread-block cluster and reduce through DSMEM, so the fp32
+// output is final ([M][ldo], one slice) instead of one slice per split
+int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages, int reduce);
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                    uint32_t box_rows);
 // out: GEMM_OUT_F32 -> float [ksplit][M][ldo]; GEMM_OUT_BF16 -> bf16 [M][ldo];
 // GEMM_OUT_SWIGLU -> bf16 [M][ldo] with N/2 columns (n_valid = ff)
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
-                int n_valid, bool pdl, cudaStream_t stream);
+                int n_valid, bool pdl, cudaStream_t stream, bool accumulate = false);
 
 }  // namespace asd

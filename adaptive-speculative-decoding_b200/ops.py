@@ -82,14 +82,16 @@ def reject_sample_host(target_logits, draft_logits, draft_tokens, u_accept, u_re
 def linear_bf16(x: torch.Tensor, w: torch.Tensor, out_mode: int = 0, ksplit: int = 0, stages: int = 0):
     """Y = X @ W^T through ``asd_linear_bf16`` (tcgen05/TMA).  out_mode 0 -> fp32 [M, N] (the K-split
     slices are summed here, in order, as the fused consumer kernels do); 1 -> bf16 [M, N];
-    2 -> SwiGLU over gate|up-interleaved rows, bf16 [M, N/2]."""
+    2 -> SwiGLU over gate|up-interleaved rows, bf16 [M, N/2]; 3 -> fp32 [M, N] reduced inside the cluster."""
     assert x.is_cuda and w.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     x, w = x.contiguous(), w.contiguous()
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K
     used = ctypes.c_int(0)
-    if out_mode == 0:
+    if out_mode == 3:
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    elif out_mode == 0:
         ks, st, tt = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
         check(lib().asd_linear_plan(M, N, K, 0, ctypes.byref(ks), ctypes.byref(st), ctypes.byref(tt)), "plan")
         nsl = ksplit if ksplit > 0 else ks.value

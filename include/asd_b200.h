@@ -86,7 +86,9 @@ ASD_API double asd_bayesian_adjustment_host(double p_hat, double n_obs, double a
  *               add+RMSNorm / RoPE kernels) sums the slices in order;
  *   out_mode 1: out bf16 [M, N] (ksplit forced to 1);
  *   out_mode 2: SwiGLU - w rows interleaved per 128-row tile as 64 gate rows then 64 up rows;
- *               out bf16 [M, N/2] = silu(gate) * up.
+ *               out bf16 [M, N/2] = silu(gate) * up;
+ *   out_mode 3: out fp32 [M, N], final: the K splits of a tile form a thread-block cluster and are
+ *               reduced through distributed shared memory in rank order (deterministic).
  *   ksplit / stages: 0 = let the library choose (single co-resident wave).
  */
 ASD_API int asd_linear_bf16(const void* x, const void* w, void* out, int M, int N, int K, int out_mode, int ksplit,
@@ -136,7 +138,8 @@ ASD_API int asd_engine_set_kv(asd_engine_t* e, void* kv_pool, int num_pages, con
  * Called (fp32 sum, in place) after the O and down projections when tp_size > 1. */
 ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_allreduce_fn);
 /* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
- * "ksplit", "stages" (0 = automatic) */
+ * "reduce" (1 in-cluster split-K reduction with fused residual add, 0 fp32 slices summed by the glue
+ * kernels), "ksplit", "stages" (0 = automatic), "profile" (0/1) */
 ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
 /* With option "profile" = 1 every launch is bracketed by CUDA events on the launching stream;
  * this call synchronises and returns the summed milliseconds and launch counts by kernel class

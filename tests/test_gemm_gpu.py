@@ -31,6 +31,24 @@ def test_linear_fp32(M, N, K, ksplit, stages):
     assert (y - ref).abs().max().item() <= 1e-3 * scale, ((y - ref).abs().max().item(), scale)
 
 
+@pytest.mark.parametrize("M,N,K,ksplit", [
+    (96, 5120, 5120, 0), (16, 3584, 3584, 0), (96, 7168, 5120, 0), (16, 3584, 18944, 0), (48, 640, 1024, 3),
+    (96, 1000, 712, 2), (5, 384, 896, 5), (128, 512, 2048, 7), (256, 384, 2048, 4), (300, 256, 1024, 2),
+    (96, 256, 512, 8), (16, 128, 4096, 6)])
+def test_linear_cluster_reduce(M, N, K, ksplit):
+    import torch
+    from asd_b200.ops import linear_bf16
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    y = linear_bf16(x, w, 3, ksplit, 0)
+    y2 = linear_bf16(x, w, 3, ksplit, 0)
+    ref = ref_fp32(x, w)
+    scale = ref.abs().max().item()
+    assert (y - ref).abs().max().item() <= 1e-3 * scale
+    assert torch.equal(y, y2)      # deterministic: fixed reduction order
+
+
 @pytest.mark.parametrize("M,N,K", [(96, 512, 1024), (16, 1152, 896), (33, 130, 256)])
 def test_linear_bf16_out(M, N, K):
     import torch

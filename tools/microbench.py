@@ -69,7 +69,7 @@ def bench_sampler(B, k, V=152064, T=0.7, copies=None):
                           GBs=round(gbs, 1), frac=round(gbs / PEAK, 3))), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and (len(sys.argv) < 2 or sys.argv[1] in ("all", "gemm", "sampler")):
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "gemm"):
         # Qwen2.5-32B verify shapes (M = 96) and 7B draft shapes (M = 16)
@@ -84,3 +84,33 @@ if __name__ == "__main__":
     if what in ("all", "sampler"):
         for B, k in [(1, 8), (16, 5), (64, 8), (256, 8), (256, 1)]:
             bench_sampler(B, k)
+
+
+def sweep():
+    shapes = [("o32", 96, 5120, 5120), ("qkv32", 96, 7168, 5120), ("down32", 96, 5120, 27648),
+              ("o7", 16, 3584, 3584), ("qkv7", 16, 4608, 3584), ("down7", 16, 3584, 18944)]
+    for name, M, N, K in shapes:
+        for ks in (1, 2, 3, 4, 6, 8, 12):
+            for st in (2, 4, 6, 7, 10):
+                if M == 96 and st > 7:
+                    continue
+                try:
+                    bench_gemm(M, N, K, 0, ksplit=ks, stages=st)
+                except AssertionError as e:
+                    print("skip", name, ks, st, e)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+    sweep()
+
+
+def bench_reduce():
+    for M, N, K in [(96, 5120, 5120), (96, 7168, 5120), (96, 5120, 27648), (16, 3584, 3584), (16, 4608, 3584),
+                    (16, 3584, 18944)]:
+        bench_gemm(M, N, K, 0)
+        for ks in (0, 2, 4, 8):
+            bench_gemm(M, N, K, 3, ksplit=ks)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "reduce":
+    bench_reduce()
