@@ -51,6 +51,7 @@ class QwenEngine:
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float() / cfg.head_dim))
         self.inv_freq = inv.to(self.device)
         self._weights = []   # keep tensors alive
+        self._index_cache = {}
         self._globals_set = False
 
     def close(self):
@@ -132,18 +133,27 @@ class QwenEngine:
         check(rc, "asd_engine_forward")
         return logits_out if n_rows else None
 
+    def _uniform_index(self, nseq: int, q: int):
+        """static index tensors of a uniform (nseq x q) call, built once per shape"""
+        key = (nseq, q)
+        c = self._index_cache.get(key)
+        if c is None:
+            ar = torch.arange(q, dtype=torch.int32, device=self.device)
+            c = dict(ar=ar[None].contiguous(),
+                     cu_q=torch.arange(0, (nseq + 1) * q, q, dtype=torch.int32, device=self.device),
+                     last_rows=torch.arange(q - 1, nseq * q, q, dtype=torch.int32, device=self.device))
+            self._index_cache[key] = c
+        return c
+
     def forward_uniform(self, tokens2d: torch.Tensor, start_pos: torch.Tensor, slots: torch.Tensor, max_kv_len: int,
                         last_only: bool = False, want_logits: bool = True, logits_out=None, logits_ld: int = 0):
         """tokens2d int32 [nseq, q]; start_pos int32 [nseq] (position of column 0); slots int32 [nseq]."""
         nseq, q = tokens2d.shape
-        ar = torch.arange(q, dtype=torch.int32, device=self.device)
-        positions = (start_pos[:, None] + ar[None]).reshape(-1).contiguous()
-        token_slot = slots[:, None].expand(nseq, q).reshape(-1).contiguous()
-        cu_q = torch.arange(0, (nseq + 1) * q, q, dtype=torch.int32, device=self.device)
-        rows = None
-        if last_only and want_logits and q > 1:
-            rows = torch.arange(q - 1, nseq * q, q, dtype=torch.int32, device=self.device)
-        return self.forward(tokens2d.reshape(-1).contiguous(), positions, token_slot, cu_q, slots.contiguous(), q,
+        ix = self._uniform_index(nseq, q)
+        positions = (start_pos[:, None] + ix["ar"]).reshape(-1)
+        token_slot = slots[:, None].expand(nseq, q).reshape(-1) if q > 1 else slots
+        rows = ix["last_rows"] if (last_only and want_logits and q > 1) else None
+        return self.forward(tokens2d.reshape(-1), positions, token_slot.contiguous(), ix["cu_q"], slots, q,
                             max_kv_len, rows, logits_out, want_logits, logits_ld)
 
     def prefill(self, prompt_ids: torch.Tensor, slots: torch.Tensor, chunk: int = 0, want_logits: bool = True):

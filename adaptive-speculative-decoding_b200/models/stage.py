@@ -1,0 +1,253 @@
+"""Engine seam.  ``Stage`` / ``StageManager`` / ``StageConfig`` are imported by the reference
+(src/serving/pipeline.py:14, src/serving/server.py:23,151-164) from ``src/models/stage.py``, a file the
+reference does not ship; the signatures below are reconstructed from those call sites and from the
+listing in docs/guides/RESEARCH_PROTOCOL.md:233-304.  Where the reference's
+Stage wraps ``vllm.LLM`` this one wraps the B200 engine: a ``QwenEngine`` target, optionally
+accelerated by a smaller draft engine through chain draft-then-verify (``SpecDecoder``)."""
+from __future__ import annotations
+
+import logging
+import threading
+import time
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .._lib import AsdError
+from .qwen2 import QWEN25, SIZE_ALIASES, Qwen2Config, get_config
+
+logger = logging.getLogger(__name__)
+
+
+class ModelLoadError(AsdError):
+    """name used by the reference at the stage boundary (real_model_pipeline.py:92,115)"""
+
+
+class InferenceError(AsdError):
+    """name used by the reference at the stage boundary (real_model_pipeline.py:120,166)"""
+
+
+COST_PER_TOKEN = {"8b": 1.0, "13b": 1.6, "34b": 4.2, "70b": 8.8,       # RESEARCH_PROTOCOL.md:255-260
+                  "7b": 1.0, "14b": 2.0, "32b": 4.5, "72b": 10.0,      # docs/papers/FINAL_PAPER.md:130-132
+                  "0.5b": 0.1, "1.5b": 0.3}
+KV_GB_PER_TOKEN = {"8b": 0.002, "13b": 0.003, "34b": 0.008, "70b": 0.016}   # RESEARCH_PROTOCOL.md:296-301
+PAD_LOGPROB = -1.0e4   # finite stand-in for "not in the top-k": exp(PAD) * PAD == -0.0, never NaN
+
+
+class FusedLogprobs(np.ndarray):
+    """ndarray [T, 5] shaped like vLLM's top-5 logprobs (col 0: emitted token, col 1: arg-max token,
+    col 2: second best, cols 3-4 padding) that also carries ``fused``: float32 [T, 6] =
+    (lse, p_max, margin, entropy, ln p(draft tok), ln p(emitted tok)) computed by the sampling kernel over
+    the FULL vocabulary (asd_b200.ops.FEATURE_NAMES)."""
+    fused: Optional[np.ndarray] = None
+
+    def __array_finalize__(self, obj):
+        self.fused = getattr(obj, "fused", None)
+
+
+def make_logprobs(emitted_lp: np.ndarray, fused: np.ndarray) -> FusedLogprobs:
+    T = len(emitted_lp)
+    a = np.full((T, 5), PAD_LOGPROB, dtype=np.float64)
+    if T:
+        pmax = np.clip(fused[:, 1].astype(np.float64), 1e-300, 1.0)
+        p2 = np.clip(pmax - fused[:, 2].astype(np.float64), 1e-300, 1.0)
+        a[:, 0], a[:, 1], a[:, 2] = emitted_lp, np.log(pmax), np.log(p2)
+    out = a.view(FusedLogprobs)
+    out.fused = np.asarray(fused, dtype=np.float32)
+    return out
+
+
+class ByteTokenizer:
+    """Offline stand-in for the HF tokenizer (no tokenizer files can be fetched here): UTF-8 bytes."""
+
+    def __init__(self, vocab_size: int):
+        self.vocab_size = vocab_size
+
+    def encode(self, text: str) -> List[int]:
+        ids = list(text.encode("utf-8")) or [0]
+        return [i % self.vocab_size for i in ids]
+
+    def decode(self, ids: List[int]) -> str:
+        return bytes(int(i) & 0xFF for i in ids).decode("utf-8", errors="replace")
+
+
+def load_tokenizer(model_name: str, vocab_size: int):
+    import os
+    if os.path.isdir(model_name):
+        try:
+            from transformers import AutoTokenizer
+            tok = AutoTokenizer.from_pretrained(model_name, local_files_only=True)
+            tok.encode_ids = lambda t: tok.encode(t, add_special_tokens=False)
+            return tok
+        except Exception as e:  # pragma: no cover - depends on local files
+            logger.warning("tokenizer at %s unusable (%s); falling back to bytes", model_name, e)
+    return ByteTokenizer(vocab_size)
+
+
+@dataclass
+class StageConfig:
+    """server.py:151-158"""
+    model_name: str
+    model_size: str
+    tensor_parallel_size: int = 1
+    gpu_memory_utilization: float = 0.8
+    quantized: bool = False
+    cost_per_token: Optional[float] = None
+
+
+class Stage:
+    """One model of the cascade.  ``generate`` keeps the reference's contract:
+    ``(texts, logprobs, stats)`` with ``stats["generation_time_ms"]`` (pipeline.py:204-209,245)."""
+
+    def __init__(self, model_name: str, model_size: str, tensor_parallel_size: int = 1,
+                 gpu_memory_utilization: float = 0.8, quantized: bool = False, *,
+                 cost_per_token: Optional[float] = None, config: Optional[Qwen2Config] = None,
+                 draft: Optional["Stage"] = None, k: int = 5, weights: Optional[dict] = None, seed: int = 0,
+                 max_batch: int = 16, max_model_len: int = 4096, device="cuda", gpu_ids: Optional[List[int]] = None):
+        self.model_name, self.model_size = model_name, model_size.lower()
+        self.tensor_parallel_size = tensor_parallel_size
+        self.gpu_memory_utilization, self.quantized = gpu_memory_utilization, quantized
+        if quantized:
+            logger.warning("quantized=True is ignored: the B200 engine runs bf16 weights")
+        if tensor_parallel_size != 1:
+            raise ModelLoadError("in-process Stage supports tensor_parallel_size == 1; tensor-parallel targets "
+                                 "are launched one process per GPU (asd_b200.parallel, bench.py --gpus N)")
+        try:
+            self.cfg = config or get_config(self.model_size)
+        except KeyError as e:
+            raise ModelLoadError(f"unknown model size {model_size!r}") from e
+        self.cost_per_token = cost_per_token if cost_per_token is not None else COST_PER_TOKEN.get(self.model_size, 1.0)
+        self.draft, self.k = draft, k
+        self.max_batch, self.max_model_len = max_batch, max_model_len
+        self.tokenizer = load_tokenizer(model_name, self.cfg.vocab_size)
+        self._lock = threading.Lock()       # the pipeline calls generate() from up to 100 threads
+        try:
+            from ..engine import QwenEngine
+            self.engine = QwenEngine(self.cfg, max_seqs=max_batch, max_seq_len=max_model_len,
+                                     max_tokens=max(256, max_batch * (k + 1)), device=device)
+            if weights is not None:
+                self.engine.load_hf_weights(weights)
+            else:
+                self.engine.load_random(seed)
+        except AsdError:
+            raise
+        except Exception as e:
+            raise ModelLoadError(f"failed to load {model_name}: {e}") from e
+
+    # ------------------------------------------------------------------ reference API
+    def generate(self, prompts: List[str], max_tokens: int = 512, temperature: float = 0.7, top_p: float = 0.9,
+                 return_logprobs: bool = True) -> Tuple[List[str], List[np.ndarray], Dict[str, float]]:
+        """top_p is accepted for signature compatibility; sampling is over the full softmax(z/T)."""
+        t0 = time.time()
+        ids = [self._encode(p) for p in prompts]
+        texts: List[Optional[str]] = [None] * len(prompts)
+        lps: List[Optional[np.ndarray]] = [None] * len(prompts)
+        acc_tok = steps = 0
+        with self._lock:
+            by_len: Dict[int, List[int]] = {}
+            for i, x in enumerate(ids):
+                by_len.setdefault(len(x), []).append(i)
+            for _, idx in by_len.items():
+                for s in range(0, len(idx), self.max_batch):
+                    grp = idx[s:s + self.max_batch]
+                    toks, lp, fused, st = self._generate_ids([ids[i] for i in grp], max_tokens, temperature)
+                    acc_tok += st["accepted"]
+                    steps += st["steps"]
+                    for j, i in enumerate(grp):
+                        texts[i] = self.tokenizer.decode(toks[j])
+                        lps[i] = make_logprobs(lp[j], fused[j]) if return_logprobs else np.array([])
+        stats = {"generation_time_ms": (time.time() - t0) * 1000.0, "draft_tokens_accepted": acc_tok,
+                 "decode_steps": steps}
+        return texts, lps, stats
+
+    def get_model_info(self) -> Dict[str, object]:
+        return {"model_name": self.model_name, "model_size": self.model_size, "parameters": self.cfg.params,
+                "tensor_parallel_size": self.tensor_parallel_size, "cost_per_token": self.cost_per_token,
+                "dtype": "bfloat16", "hidden_size": self.cfg.hidden_size, "num_layers": self.cfg.num_hidden_layers,
+                "draft": None if self.draft is None else self.draft.model_size, "engine": "asd_b200 (sm_100a)"}
+
+    def compute_kv_cache_size(self, seq_len: int) -> float:
+        """GB of KV cache for one sequence (exact for the Qwen2.5 shape; the reference's listing uses a
+        per-size constant, RESEARCH_PROTOCOL.md:292-303)."""
+        if self.model_size in KV_GB_PER_TOKEN and self.model_size not in QWEN25:
+            return seq_len * KV_GB_PER_TOKEN[self.model_size]
+        return seq_len * self.cfg.kv_bytes_per_token() / 1e9
+
+    # ------------------------------------------------------------------ internals
+    def _encode(self, text: str) -> List[int]:
+        enc = getattr(self.tokenizer, "encode_ids", None) or self.tokenizer.encode
+        ids = list(enc(text))
+        return ids[-(self.max_model_len // 2):] or [0]
+
+    def _generate_ids(self, prompts: List[List[int]], max_tokens: int, temperature: float):
+        import torch
+        from ..engine import SpecDecoder
+        B, P = len(prompts), len(prompts[0])
+        max_new = max(1, min(max_tokens, self.max_model_len - P - self.k - 2))
+        dec = SpecDecoder(self.engine, None if self.draft is None else self.draft.engine, B, self.k, temperature)
+        try:
+            first = dec.prefill(torch.tensor(prompts, dtype=torch.int32))
+        except AsdError as e:
+            raise InferenceError(str(e)) from e
+        toks = [[int(t)] for t in first.cpu().tolist()]
+        lp = [[0.0] for _ in range(B)]
+        fused = [[np.zeros(6, np.float32)] for _ in range(B)]
+        accepted = steps = 0
+        while min(len(t) for t in toks) < max_new:
+            out = dec.step()
+            steps += 1
+            ot, n = out["out_tokens"].cpu().numpy(), out["accepted_len"].cpu().numpy()
+            ol, of = out["out_logprobs"].cpu().numpy(), out["features"].cpu().numpy()
+            accepted += int(n.sum())
+            for b in range(B):
+                m = int(n[b]) + 1
+                toks[b] += [int(x) for x in ot[b, :m]]
+                lp[b] += [float(x) for x in ol[b, :m]]
+                fused[b] += [of[b, i] for i in range(m)]
+        toks = [t[:max_new] for t in toks]
+        return (toks, [np.asarray(x[:max_new]) for x in lp], [np.stack(f[:max_new]) for f in fused],
+                {"accepted": accepted, "steps": steps})
+
+
+class StageManager:
+    """server.py:163-164, pipeline.py:185: ``StageManager(stage_configs, gpu_allocation).get_stage(name)``.
+    Stages are keyed by size label; the reference's Llama-era labels (8b/13b/34b/70b, pipeline.py:175)
+    resolve to the Qwen2.5 cascade it describes (7b/14b/32b/72b).  Each stage drafts with the previous
+    (smaller) stage when ``speculative=True``."""
+
+    def __init__(self, stage_configs: List[StageConfig], gpu_allocation: Optional[Dict[str, List[int]]] = None, *,
+                 speculative: bool = True, k: int = 5, stage_kwargs: Optional[dict] = None):
+        self.gpu_allocation = gpu_allocation or {}
+        self.stages: Dict[str, Stage] = {}
+        self.order: List[str] = []
+        prev: Optional[Stage] = None
+        for i, sc in enumerate(stage_configs):
+            gpus = self.gpu_allocation.get(sc.model_size, [0])
+            kw = dict(stage_kwargs or {})
+            st = Stage(sc.model_name, sc.model_size, sc.tensor_parallel_size, sc.gpu_memory_utilization, sc.quantized,
+                       cost_per_token=sc.cost_per_token, draft=prev if speculative else None, k=k, seed=i,
+                       device=f"cuda:{gpus[0]}" if gpus else "cuda", gpu_ids=gpus, **kw)
+            key = sc.model_size.lower()
+            self.stages[key] = st
+            self.order.append(key)
+            prev = st
+
+    def get_stage(self, name: str) -> Stage:
+        key = name.lower()
+        if key in self.stages:
+            return self.stages[key]
+        alias = SIZE_ALIASES.get(key)
+        if alias in self.stages:
+            return self.stages[alias]
+        rev = {v: k for k, v in SIZE_ALIASES.items()}
+        if rev.get(key) in self.stages:
+            return self.stages[rev[key]]
+        raise KeyError(f"no stage named {name!r}; have {list(self.stages)}")
+
+    def stage_names(self) -> List[str]:
+        return list(self.order)
+
+    def warmup_all(self):
+        for st in self.stages.values():
+            st.generate(["warmup"], max_tokens=4, temperature=0.0)

@@ -10,3 +10,23 @@ __path__.insert(0, _real)
 from ._lib import lib, library_path  # noqa: E402,F401
 
 __all__ = ["lib", "library_path"]
+
+
+def install_as_src():
+    """Register this package under the reference's module names (``src.serving.pipeline``,
+    ``src.models.stage``, ``src.models.predictor``, ``src.algorithms.dp_solver``, ...) so that code written
+    against sa2shun/adaptive-speculative-decoding imports the B200 implementation unchanged."""
+    import importlib
+    import sys
+    import types
+    names = ["algorithms", "algorithms.dp_solver", "models", "models.stage", "models.predictor", "serving",
+             "serving.pipeline", "serving.cache_manager", "serving.real_model_pipeline", "theory",
+             "theory.optimal_stopping"]
+    root = sys.modules.setdefault("src", types.ModuleType("src"))
+    root.__path__ = []
+    for n in names:
+        mod = importlib.import_module(f"asd_b200.{n}")
+        sys.modules[f"src.{n}"] = mod
+        parent, _, leaf = n.rpartition(".")
+        setattr(sys.modules[f"src.{parent}"] if parent else root, leaf, mod)
+    return root

@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference API: pipeline control flow against goldens produced by the
+reference's UNMODIFIED src/serving/pipeline.py (oracle/gen_golden.py), threshold policy, cache manager."""
+import asyncio
+import types
+
+import numpy as np
+import pytest
+
+from asd_b200.algorithms import dp_solver
+from asd_b200.serving.cache_manager import KVCacheManager
+from asd_b200.serving.pipeline import (AdaptiveSpeculativePipeline, PipelineConfig, RequestResult)
+from asd_b200.theory.optimal_stopping import OptimalStoppingTheory, TheoreticalParameters
+from conftest import fh
+
+
+class FakeStage:
+    def __init__(self, name, cost):
+        self.name, self.cost_per_token, self.calls = name, cost, 0
+
+    def generate(self, prompts, max_tokens=512, temperature=0.7, top_p=0.9, return_logprobs=True):
+        self.calls += 1
+        return ([f"{self.name}-says: " + p[:16] for p in prompts], [np.full((3, 5), -1.0)], {"generation_time_ms": 1.0})
+
+
+class FakeManager:
+    def __init__(self, names=("8b", "13b", "34b", "70b"), costs=(1.0, 1.6, 4.2, 8.8)):
+        self.stages = {n: FakeStage(n, c) for n, c in zip(names, costs)}
+        self._names = list(names)
+
+    def get_stage(self, name):
+        return self.stages[name]
+
+    def stage_names(self):
+        return list(self._names)
+
+
+class SeqPredictor:
+    def __init__(self, seq):
+        self.seq, self.i = seq, 0
+
+    def predict(self, prompt, draft_output, draft_logprobs, stage_id, feature_extractor=None):
+        v = self.seq[self.i % len(self.seq)]
+        self.i += 1
+        return v
+
+
+def test_reference_compat_matches_unmodified_reference_pipeline(stop_rule_golden):
+    for g in stop_rule_golden["pipeline"]:
+        cfg = PipelineConfig(lambda_value=fh(g["lam"]), risk_adjustment=g["risk_adjustment"], enable_caching=False,
+                             reference_compat=True)
+        pipe = AdaptiveSpeculativePipeline(FakeManager(), SeqPredictor([fh(x) for x in g["predictions"]]), None, cfg)
+        r = pipe.process_request("What is the capital of France?", max_tokens=8, temperature=0.7, request_id="golden")
+        pipe.shutdown()
+        assert r.output == g["output"] and r.stopped_at_stage == g["stopped_at_stage"]
+        assert [float(x).hex() for x in r.stage_probabilities] == g["stage_probabilities"]
+        assert [float(x).hex() for x in r.stage_costs] == g["stage_costs"]
+        assert r.total_tokens == g["total_tokens"] and r.cache_hits == g["cache_hits"]
+
+
+def test_default_mode_escalates_and_stops_with_the_full_vector_rule():
+    mgr = FakeManager(("7b", "32b", "72b"), (1.0, 4.5, 10.0))
+    # confident draft: stop at stage 0
+    pipe = AdaptiveSpeculativePipeline(mgr, SeqPredictor([0.99]), None, PipelineConfig(lambda_value=1.0,
+                                                                                       risk_adjustment=False))
+    assert pipe.process_request("q").stopped_at_stage == 0
+    # unsure draft, high quality weight: escalate.  The rule's penalty lam * (1 - prod p) can only shrink by
+    # reaching the last stage (J[L] = 0), so once stage 0 continues the cascade runs to the end.
+    pipe = AdaptiveSpeculativePipeline(mgr, SeqPredictor([0.2, 0.95]), None, PipelineConfig(lambda_value=20.0,
+                                                                                            risk_adjustment=False))
+    r = pipe.process_request("q")
+    assert r.stopped_at_stage == 2 and r.output.startswith("72b-says") and r.stage_costs == [1.0, 4.5, 10.0]
+    assert mgr.stages["32b"].calls == 1
+    # nobody is confident: run to the last stage
+    pipe = AdaptiveSpeculativePipeline(mgr, SeqPredictor([0.1, 0.1]), None, PipelineConfig(lambda_value=50.0,
+                                                                                           risk_adjustment=False))
+    r = pipe.process_request("q")
+    assert r.stopped_at_stage == 2 and r.stage_probabilities[-1] == 1.0
+    # decisions agree with the DP evaluated by hand
+    k, _ = dp_solver.optimal_stopping_rule([0.2, 1.0, 1.0], [1.0, 4.5, 10.0], 20.0)
+    assert k > 0
+    stats = pipe.get_stats()
+    assert stats["total_requests"] == 1 and stats["stage_stops"][2] == 1 and "cache_stats" in stats
+    assert r["latency_ms"] == r.latency_ms and r["costs"] == r.stage_costs
+    pipe.update_lambda(3.0)
+    assert pipe.lambda_value == 3.0
+    pipe.reset_stats()
+    assert pipe.get_stats()["total_requests"] == 0
+    pipe.shutdown()
+
+
+def test_async_batch_and_error_path():
+    mgr = FakeManager(("7b", "32b"), (1.0, 4.5))
+    pipe = AdaptiveSpeculativePipeline(mgr, SeqPredictor([0.9]), None, PipelineConfig())
+    r = asyncio.run(pipe.process_request_async("hello"))
+    assert isinstance(r, RequestResult)
+    assert len(pipe.batch_process(["a", "b", "c"])) == 3
+
+    class Boom(FakeStage):
+        def generate(self, *a, **k):
+            raise RuntimeError("engine failure")
+    mgr.stages["7b"] = Boom("7b", 1.0)
+    with pytest.raises(RuntimeError):
+        pipe.process_request("x")
+    assert pipe.get_stats()["error_count"] == 1 and pipe.get_stats()["active_requests"] == 0
+    pipe.shutdown()
+
+
+def test_cache_manager_api():
+    cm = KVCacheManager(max_cache_size_gb=1e-6, cleanup_interval=3600)      # ~1 KB budget
+    assert cm.allocate("r1", 0, {"output": "x" * 300, "logprobs": np.zeros(10)})
+    assert cm.get_cache("r1", 0)["output"].startswith("x") and cm.get_cache("r1", 1) is None
+    assert cm.allocate("r2", 0, {"output": "y" * 600})
+    assert cm.allocate("r3", 0, {"output": "z" * 600})                      # forces LRU eviction
+    assert cm.get_stats()["current_size_bytes"] <= cm.max_cache_size_bytes
+    assert not cm.allocate("big", 0, {"output": "w" * 5000})
+    cm.allocate("r4", 0, {"output": "a"}); cm.allocate("r4", 1, {"output": "b"}); cm.allocate("r4", 2, {"output": "c"})
+    cm.truncate_at_stage("r4", 0)
+    assert cm.get_cache("r4", 0) is not None and cm.get_cache("r4", 2) is None
+    cm.cleanup_request("r4")                                                # str payloads do not crash
+    st = cm.get_stats()
+    assert st["hit_rate"] > 0 and "utilization" in st
+    cm.shutdown()
+
+
+def test_threshold_policy_matches_reference(stop_rule_golden):
+    for g in stop_rule_golden["policy"]:
+        q, c = [fh(x) for x in g["quality_bounds"]], [fh(x) for x in g["cost_ratios"]]
+        th = OptimalStoppingTheory(TheoreticalParameters(n_stages=len(q), quality_bounds=q, cost_ratios=c,
+                                                         lambda_param=fh(g["lam"]))).derive_optimal_policy()
+        assert {str(s): float(v).hex() for s, v in th.items()} == g["thresholds"]
+    d = OptimalStoppingTheory(TheoreticalParameters()).derive_optimal_policy()
+    assert d == {3: 0, 2: -0.7076923076923076, 1: -0.4714285714285714, 0: -0.09999999999999998}
+
+
+def test_feature_extractor_and_predictor_follow_the_listing():
+    from asd_b200.models.predictor import FeatureExtractor, QualityPredictor
+    from asd_b200.models.stage import make_logprobs
+    lp = np.log(np.array([[0.5, 0.2, 0.1, 0.1, 0.1], [0.9, 0.05, 0.02, 0.02, 0.01]]))
+    f = FeatureExtractor().extract("a b c", "d e", lp, 2)
+    assert f.shape == (256,) and (f[5:] == 0).all()
+    ent = -np.mean([np.sum(np.exp(r) * r) for r in lp])
+    np.testing.assert_allclose(f[:5], [ent, 3 / 2048, 2 / 512, np.mean(lp.max(1)), 0.5])
+    assert FeatureExtractor().extract("a", "", np.zeros((0, 5)), 0)[3] == -10.0
+    fused = np.array([[1.0, 0.5, 0.3, 1.2, -1.0, -0.7], [1.0, 0.9, 0.85, 0.3, -0.1, -0.1]], np.float32)
+    flp = make_logprobs(np.array([-0.7, -0.1]), fused)
+    assert flp.shape == (2, 5) and flp.fused is not None and flp[-32:].fused is not None
+    g = FeatureExtractor().extract("a b c", "d e", flp, 1)
+    np.testing.assert_allclose(g[0], 0.75, rtol=1e-6)          # mean fused entropy
+    np.testing.assert_allclose(g[5:8], [0.575, -0.4, -0.7], rtol=1e-6)
+    p = QualityPredictor(feature_dim=256)
+    v = p.predict(prompt="a b", draft_output="c", draft_logprobs=flp, stage_id=0, feature_extractor=FeatureExtractor())
+    assert 0.0 < v < 1.0
+    assert sum(x.numel() for x in p.parameters()) == 33025
+    assert 0.0 < QualityPredictor({"feature_dim": 128}).predict(np.zeros(128, np.float32)) < 1.0
+
+
+def test_install_as_src_aliases():
+    import asd_b200
+    asd_b200.install_as_src()
+    from src.algorithms.dp_solver import optimal_stopping_rule
+    from src.serving.pipeline import AdaptiveSpeculativePipeline as P2
+    from src.models.stage import Stage, StageManager  # noqa: F401
+    from src.models.predictor import QualityPredictor, FeatureExtractor  # noqa: F401
+    assert P2 is AdaptiveSpeculativePipeline and optimal_stopping_rule([1.0], [1.0], 5.0) == (0, [1.0, 0.0])
