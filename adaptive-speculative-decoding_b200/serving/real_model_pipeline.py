@@ -81,11 +81,12 @@ def _size_from_name(name: str) -> str:
 
 
 class RealModelStage:
-    def __init__(self, config: StageConfig, stage_id: int, draft: Optional["RealModelStage"] = None, **stage_kwargs):
+    def __init__(self, config: StageConfig, stage_id: int, draft: Optional["RealModelStage"] = None,
+                 stage_kwargs: Optional[dict] = None):
         self.config, self.stage_id = config, stage_id
         self.model: Optional[Stage] = None
         self.is_loaded = False
-        self._draft, self._kw = draft, stage_kwargs
+        self._draft, self._kw = draft, dict(stage_kwargs or {})
         self.logger = logging.getLogger(f"stage_{stage_id}")
 
     def load_model(self):
@@ -131,11 +132,11 @@ class RealModelStage:
 
 class RealModelPipeline:
     def __init__(self, stage_configs: List[StageConfig], lambda_param: float = 1.0, speculative: bool = True,
-                 predictor: Optional[QualityPredictor] = None, **stage_kwargs):
+                 predictor: Optional[QualityPredictor] = None, stage_kwargs: Optional[dict] = None):
         self.stages: List[RealModelStage] = []
         for i, sc in enumerate(stage_configs):
             self.stages.append(RealModelStage(sc, i, self.stages[-1] if (speculative and self.stages) else None,
-                                              **stage_kwargs))
+                                              stage_kwargs))
         self.lambda_param = lambda_param
         self.quality_predictor = predictor or QualityPredictor({"feature_dim": 128})
         self.dp_solver: Optional[DynamicProgrammingSolver] = None

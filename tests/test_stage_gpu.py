@@ -57,7 +57,7 @@ def test_pipeline_end_to_end_on_engines():
 def test_real_model_pipeline_surface():
     from asd_b200.serving.real_model_pipeline import InferenceRequest, RealModelPipeline, StageConfig
     scs = [StageConfig("qwen-7b", "none", 1, [0], 256, "bfloat16"), StageConfig("qwen-32b", "none", 1, [0], 256, "bfloat16")]
-    pipe = RealModelPipeline(scs, config=tiny_config(), max_batch=2, k=2)
+    pipe = RealModelPipeline(scs, stage_kwargs=dict(config=tiny_config(), max_batch=2, k=2))
     with pytest.raises(RuntimeError):
         pipe.infer_adaptive(InferenceRequest("x", 4))
     pipe.initialize()
