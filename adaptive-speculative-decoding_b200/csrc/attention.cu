@@ -8,6 +8,10 @@
 //   * QK^T and PV run on tensor cores (mma.sync m16n8k16 bf16 -> fp32; 30..72 query rows cannot fill a
 //     128-row tcgen05 tile and the kernel is bound by the KV stream, not by math), operands staged
 //     with cp.async into XOR-swizzled shared memory and read with ldmatrix;
+//   * with few query rows (draft steps: 7 rows) the warps of a CTA share the rows and split every
+//     64-key tile between them, then merge through shared memory, so that a CTA always has 4+ warps
+//     issuing loads; the last CTA of a (sequence, kv head) to finish merges the kv splits (atomic
+//     ticket), so there is no separate combine launch;
 //   * K/V were appended in place by qkv_rope_kernel before this kernel runs; rejected speculative
 //     positions are simply overwritten by the next step (rollback = not advancing the length).
 // attn_simple_kernel is a one-warp-per-(token, head) restatement used to cross-check the tensor-core
@@ -99,22 +103,28 @@ struct AttnArgs {
     const int* cu_q;               // [nseq + 1] token ranges
     const int* seq_slot;           // [nseq]
     const int* page_table;
-    int max_pages, nh, nkv, page_size, split_keys, nsplit_max;
+    int max_pages, nh, nkv, page_size, split_keys, nsplit_max, rg_count, kg_count;
     float scale_log2;
     float* o_part;                 // [M, nh, nsplit_max, hd]
     float* ml_part;                // [M, nh, nsplit_max, 2]
+    int* tickets;                  // [nseq_max * nkv], zero between launches
+    __nv_bfloat16* out;            // [M, nh, hd]
 };
 
-// HD = head_dim (64 or 128).  blockDim = 32 * warps, each warp owns 16 query rows.
-template <int HD>
+// HD = head_dim (64 or 128); KW = keys of each 64-key tile handled by one warp (64, 32 or 16).
+// warp w = (row group w % rg_count, key group w / rg_count): 16 query rows x KW keys per tile.
+template <int HD, int KW>
 __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     constexpr int CH = HD / 8;          // 16-byte chunks per row
     constexpr int ROWB = HD * 2;        // bytes per row
     constexpr int KB = HD / 16;         // k-blocks over head_dim
+    constexpr int NT = KW / 8;          // score n-tiles per warp
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int s_last;
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sQ = smem_raw;                                   // [nwarps*16][HD]
-    uint8_t* sK = sQ + (size_t)nwarps * 16 * ROWB;            // [2][64][HD]
+    const int rg = warp % a.rg_count, kg = warp / a.rg_count;
+    uint8_t* sQ = smem_raw;                                   // [rg_count*16][HD]
+    uint8_t* sK = sQ + (size_t)a.rg_count * 16 * ROWB;        // [2][64][HD]
     uint8_t* sV = sK + 2 * kKeyTile * ROWB;                   // [2][64][HD]
     const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
 
@@ -127,11 +137,13 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     const int kbeg = sp * a.split_keys;
     if (kbeg >= kv_len) return;
     const int kend = min(kv_len, kbeg + a.split_keys);
+    const int nsplit_seq = (kv_len + a.split_keys - 1) / a.split_keys;
     const int slot = a.seq_slot[seq];
     const int* pt = a.page_table + (size_t)slot * a.max_pages;
+    grid_dep_launch();
 
     // ---- stage Q (rows r = t*G + gq -> token q0+t, head g*G+gq), swizzled
-    for (int c = threadIdx.x; c < nwarps * 16 * CH; c += blockDim.x) {
+    for (int c = threadIdx.x; c < a.rg_count * 16 * CH; c += blockDim.x) {
         const int r = c / CH, ch = c - r * CH;
         const bool ok = r < R;
         const int t = ok ? r / G : 0, gq = ok ? r - t * G : 0;
@@ -156,15 +168,13 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     load_tile(0, 0);
     cp_async_commit();
 
-    // per-thread rows
-    const int r0 = warp * 16 + (lane >> 2), r1 = r0 + 8;
+    const int r0 = rg * 16 + (lane >> 2), r1 = r0 + 8;
     const int qpos0 = kv_len - qlen + (r0 < R ? r0 / G : 0), qpos1 = kv_len - qlen + (r1 < R ? r1 / G : 0);
     float o[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
     float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     uint32_t qf[KB][4];
-    bool q_loaded = false;
 
     for (int tile = 0; tile < ntiles; ++tile) {
         const int buf = tile & 1;
@@ -172,146 +182,238 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        if (!q_loaded) {
+        if (tile == 0) {
             const int mi = lane >> 3;
-            const int row = warp * 16 + (lane & 7) + (mi & 1) * 8;
+            const int row = rg * 16 + (lane & 7) + (mi & 1) * 8;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
                 const int ch = kb * 2 + (mi >> 1);
                 ldsm_x4(uQ + row * ROWB + ((ch ^ (row & 7)) << 4), qf[kb]);
             }
-            q_loaded = true;
         }
-        // ---- S = Q K^T for 64 keys
-        float s[kKeyTile / 8][4];
+        const int key0 = kg * KW;  // first key of this warp inside the tile
+        if (kbeg + tile * kKeyTile + key0 < kend) {   // warp-uniform: skip key groups past the end
+            float s[NT][4];
 #pragma unroll
-        for (int i = 0; i < kKeyTile / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f;
-        const uint32_t kb_base = uK + buf * kKeyTile * ROWB, vb_base = uV + buf * kKeyTile * ROWB;
+            for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f;
+            const uint32_t kb_base = uK + buf * kKeyTile * ROWB, vb_base = uV + buf * kKeyTile * ROWB;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
+            for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-            for (int np = 0; np < kKeyTile / 16; ++np) {
-                const int mi = lane >> 3;
-                const int row = np * 16 + (lane & 7) + (mi >> 1) * 8;
-                const int ch = kb * 2 + (mi & 1);
-                uint32_t b[4];
-                ldsm_x4(kb_base + row * ROWB + ((ch ^ (row & 7)) << 4), b);
-                mma_bf16(s[np * 2], qf[kb], b[0], b[1]);
-                mma_bf16(s[np * 2 + 1], qf[kb], b[2], b[3]);
+                for (int np = 0; np < KW / 16; ++np) {
+                    const int mi = lane >> 3;
+                    const int row = key0 + np * 16 + (lane & 7) + (mi >> 1) * 8;
+                    const int ch = kb * 2 + (mi & 1);
+                    uint32_t b[4];
+                    ldsm_x4(kb_base + row * ROWB + ((ch ^ (row & 7)) << 4), b);
+                    mma_bf16(s[np * 2], qf[kb], b[0], b[1]);
+                    mma_bf16(s[np * 2 + 1], qf[kb], b[2], b[3]);
+                }
             }
-        }
-        // ---- mask, scale, online softmax
-        const int jbase = kbeg + tile * kKeyTile + (lane & 3) * 2;
-        float tm0 = -INFINITY, tm1 = -INFINITY;
+            const int jbase = kbeg + tile * kKeyTile + key0 + (lane & 3) * 2;
+            float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < kKeyTile / 8; ++i) {
+            for (int i = 0; i < NT; ++i) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = jbase + i * 8 + e;
-                const bool in = j < kend;
-                s[i][e] = (in && r0 < R && j <= qpos0) ? s[i][e] * a.scale_log2 : -INFINITY;
-                s[i][2 + e] = (in && r1 < R && j <= qpos1) ? s[i][2 + e] * a.scale_log2 : -INFINITY;
-                tm0 = fmaxf(tm0, s[i][e]);
-                tm1 = fmaxf(tm1, s[i][2 + e]);
+                for (int e = 0; e < 2; ++e) {
+                    const int j = jbase + i * 8 + e;
+                    const bool in = j < kend;
+                    s[i][e] = (in && r0 < R && j <= qpos0) ? s[i][e] * a.scale_log2 : -INFINITY;
+                    s[i][2 + e] = (in && r1 < R && j <= qpos1) ? s[i][2 + e] * a.scale_log2 : -INFINITY;
+                    tm0 = fmaxf(tm0, s[i][e]);
+                    tm1 = fmaxf(tm1, s[i][2 + e]);
+                }
             }
-        }
-        tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
-        tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
-        tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
-        tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
-        const float mn0 = fmaxf(mx0, tm0), mn1 = fmaxf(mx1, tm1);
-        // rows with nothing visible yet keep a finite reference so exp2f never sees (-inf) - (-inf)
-        const float ref0 = mn0 == -INFINITY ? 0.0f : mn0, ref1 = mn1 == -INFINITY ? 0.0f : mn1;
-        const float c0 = exp2f(mx0 - ref0), c1 = exp2f(mx1 - ref1);
-        float ps0 = 0.0f, ps1 = 0.0f;
-        uint32_t pf[kKeyTile / 16][4];
+            tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+            tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+            tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+            tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+            const float mn0 = fmaxf(mx0, tm0), mn1 = fmaxf(mx1, tm1);
+            const float ref0 = mn0 == -INFINITY ? 0.0f : mn0, ref1 = mn1 == -INFINITY ? 0.0f : mn1;
+            const float c0 = exp2f(mx0 - ref0), c1 = exp2f(mx1 - ref1);
+            float ps0 = 0.0f, ps1 = 0.0f;
+            uint32_t pf[KW / 16][4];
 #pragma unroll
-        for (int i = 0; i < kKeyTile / 8; ++i) {
-            const float p00 = exp2f(s[i][0] - ref0), p01 = exp2f(s[i][1] - ref0);
-            const float p10 = exp2f(s[i][2] - ref1), p11 = exp2f(s[i][3] - ref1);
-            ps0 += p00 + p01;
-            ps1 += p10 + p11;
-            pf[i >> 1][(i & 1) * 2] = pack_bf16(p00, p01);
-            pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16(p10, p11);
-        }
-        l0 = l0 * c0 + ps0;
-        l1 = l1 * c1 + ps1;
-        mx0 = mn0;
-        mx1 = mn1;
+            for (int i = 0; i < NT; ++i) {
+                const float p00 = exp2f(s[i][0] - ref0), p01 = exp2f(s[i][1] - ref0);
+                const float p10 = exp2f(s[i][2] - ref1), p11 = exp2f(s[i][3] - ref1);
+                ps0 += p00 + p01;
+                ps1 += p10 + p11;
+                pf[i >> 1][(i & 1) * 2] = pack_bf16(p00, p01);
+                pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16(p10, p11);
+            }
+            l0 = l0 * c0 + ps0;
+            l1 = l1 * c1 + ps1;
+            mx0 = mn0;
+            mx1 = mn1;
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
-            o[i][0] *= c0;
-            o[i][1] *= c0;
-            o[i][2] *= c1;
-            o[i][3] *= c1;
-        }
-        // ---- O += P V
+            for (int i = 0; i < HD / 8; ++i) {
+                o[i][0] *= c0;
+                o[i][1] *= c0;
+                o[i][2] *= c1;
+                o[i][3] *= c1;
+            }
 #pragma unroll
-        for (int kk = 0; kk < kKeyTile / 16; ++kk) {
+            for (int kk = 0; kk < KW / 16; ++kk) {
 #pragma unroll
-            for (int dn = 0; dn < HD / 16; ++dn) {
-                const int mi = lane >> 3;
-                const int row = kk * 16 + (lane & 7) + (mi & 1) * 8;
-                const int ch = dn * 2 + (mi >> 1);
-                uint32_t b[4];
-                ldsm_x4_t(vb_base + row * ROWB + ((ch ^ (row & 7)) << 4), b);
-                mma_bf16(o[dn * 2], pf[kk], b[0], b[1]);
-                mma_bf16(o[dn * 2 + 1], pf[kk], b[2], b[3]);
+                for (int dn = 0; dn < HD / 16; ++dn) {
+                    const int mi = lane >> 3;
+                    const int row = key0 + kk * 16 + (lane & 7) + (mi & 1) * 8;
+                    const int ch = dn * 2 + (mi >> 1);
+                    uint32_t b[4];
+                    ldsm_x4_t(vb_base + row * ROWB + ((ch ^ (row & 7)) << 4), b);
+                    mma_bf16(o[dn * 2], pf[kk], b[0], b[1]);
+                    mma_bf16(o[dn * 2 + 1], pf[kk], b[2], b[3]);
+                }
             }
         }
         __syncthreads();  // everyone done with this buffer before it is refilled
     }
     cp_async_wait<0>();
-    // ---- partial results (unnormalised O, row max, row sum)
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-#pragma unroll
-    for (int hrow = 0; hrow < 2; ++hrow) {
-        const int r = hrow ? r1 : r0;
-        if (r >= R) continue;
-        const int t = r / G, gq = r - t * G;
-        const size_t idx = (((size_t)(q0 + t) * a.nh + g * G + gq) * a.nsplit_max + sp);
-        float* op = a.o_part + idx * HD;
+
+    // ---- merge the key groups of a row group through shared memory (K/V ring is idle now)
+    float* xo = reinterpret_cast<float*>(sK);                 // [nwarps][16][HD]
+    float* xml = xo + (size_t)nwarps * 16 * HD;               // [nwarps][16][2]
+    if (a.kg_count > 1) {
+        __syncthreads();
+        float* wo = xo + (size_t)warp * 16 * HD;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i) {
             const int d = i * 8 + (lane & 3) * 2;
-            *reinterpret_cast<float2*>(op + d) = make_float2(o[i][hrow * 2], o[i][hrow * 2 + 1]);
+            *reinterpret_cast<float2*>(wo + (lane >> 2) * HD + d) = make_float2(o[i][0], o[i][1]);
+            *reinterpret_cast<float2*>(wo + ((lane >> 2) + 8) * HD + d) = make_float2(o[i][2], o[i][3]);
         }
         if ((lane & 3) == 0) {
-            a.ml_part[idx * 2] = hrow ? mx1 : mx0;
-            a.ml_part[idx * 2 + 1] = hrow ? l1 : l0;
+            xml[(warp * 16 + (lane >> 2)) * 2] = mx0;
+            xml[(warp * 16 + (lane >> 2)) * 2 + 1] = l0;
+            xml[(warp * 16 + (lane >> 2) + 8) * 2] = mx1;
+            xml[(warp * 16 + (lane >> 2) + 8) * 2 + 1] = l1;
+        }
+        __syncthreads();
+        if (kg == 0) {
+            float m0 = mx0, m1 = mx1;
+            for (int k2 = 1; k2 < a.kg_count; ++k2) {
+                const int w2 = k2 * a.rg_count + rg;
+                m0 = fmaxf(m0, xml[(w2 * 16 + (lane >> 2)) * 2]);
+                m1 = fmaxf(m1, xml[(w2 * 16 + (lane >> 2) + 8) * 2]);
+            }
+            const float f0 = m0 == -INFINITY ? 0.0f : m0, f1 = m1 == -INFINITY ? 0.0f : m1;
+            float sc0 = exp2f(mx0 - f0), sc1 = exp2f(mx1 - f1);
+            l0 *= sc0;
+            l1 *= sc1;
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) {
+                o[i][0] *= sc0;
+                o[i][1] *= sc0;
+                o[i][2] *= sc1;
+                o[i][3] *= sc1;
+            }
+            for (int k2 = 1; k2 < a.kg_count; ++k2) {
+                const int w2 = k2 * a.rg_count + rg;
+                const float* po = xo + (size_t)w2 * 16 * HD;
+                sc0 = exp2f(xml[(w2 * 16 + (lane >> 2)) * 2] - f0);
+                sc1 = exp2f(xml[(w2 * 16 + (lane >> 2) + 8) * 2] - f1);
+                l0 += xml[(w2 * 16 + (lane >> 2)) * 2 + 1] * sc0;
+                l1 += xml[(w2 * 16 + (lane >> 2) + 8) * 2 + 1] * sc1;
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) {
+                    const int d = i * 8 + (lane & 3) * 2;
+                    const float2 a0 = *reinterpret_cast<const float2*>(po + (lane >> 2) * HD + d);
+                    const float2 a1 = *reinterpret_cast<const float2*>(po + ((lane >> 2) + 8) * HD + d);
+                    o[i][0] += a0.x * sc0;
+                    o[i][1] += a0.y * sc0;
+                    o[i][2] += a1.x * sc1;
+                    o[i][3] += a1.y * sc1;
+                }
+            }
+            mx0 = m0;
+            mx1 = m1;
         }
     }
-}
-
-// one CTA per (token, head): merge the kv splits
-__global__ void attn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part,
-                                    const int* __restrict__ positions, int split_keys, int nsplit_max, int hd,
-                                    __nv_bfloat16* __restrict__ out, int nh) {
-    grid_dep_launch();
-    const int m = blockIdx.x, hq = blockIdx.y;
-    const int ns = min(nsplit_max, (positions[m] + split_keys) / split_keys);  // ceil((pos+1)/split)
-    const size_t base = ((size_t)m * nh + hq) * nsplit_max;
-    float mx = -INFINITY;
-    for (int s = 0; s < ns; ++s) mx = fmaxf(mx, ml_part[(base + s) * 2]);
-    float l = 0.0f;
-    for (int s = 0; s < ns; ++s) l += ml_part[(base + s) * 2 + 1] * exp2f(ml_part[(base + s) * 2] - mx);
-    for (int d = threadIdx.x; d < hd; d += blockDim.x) {
-        float acc = 0.0f;
-        for (int s = 0; s < ns; ++s) acc += o_part[(base + s) * hd + d] * exp2f(ml_part[(base + s) * 2] - mx);
-        out[((size_t)m * nh + hq) * hd + d] = __float2bfloat16(acc / l);
+    // ---- results: final output when the sequence has a single split, else partials + last-CTA combine
+    if (kg == 0) {
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int r = hrow ? r1 : r0;
+            if (r >= R) continue;
+            const int t = r / G, gq = r - t * G;
+            const size_t th = (size_t)(q0 + t) * a.nh + g * G + gq;
+            const float l = hrow ? l1 : l0;
+            if (nsplit_seq == 1) {
+                __nv_bfloat16* op = a.out + th * HD;
+                const float inv = 1.0f / l;
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) {
+                    const int d = i * 8 + (lane & 3) * 2;
+                    *reinterpret_cast<__nv_bfloat162*>(op + d) =
+                        __floats2bfloat162_rn(o[i][hrow * 2] * inv, o[i][hrow * 2 + 1] * inv);
+                }
+            } else {
+                const size_t idx = th * a.nsplit_max + sp;
+                float* op = a.o_part + idx * HD;
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) {
+                    const int d = i * 8 + (lane & 3) * 2;
+                    *reinterpret_cast<float2*>(op + d) = make_float2(o[i][hrow * 2], o[i][hrow * 2 + 1]);
+                }
+                if ((lane & 3) == 0) {
+                    a.ml_part[idx * 2] = hrow ? mx1 : mx0;
+                    a.ml_part[idx * 2 + 1] = l;
+                }
+            }
+        }
     }
-}
-
-int attn_workspace_floats(int M, int nh, int hd, int nsplit_max, size_t* o_floats, size_t* ml_floats) {
-    *o_floats = (size_t)M * nh * nsplit_max * hd;
-    *ml_floats = (size_t)M * nh * nsplit_max * 2;
-    return 0;
+    if (nsplit_seq == 1) return;
+    // the last CTA of this (sequence, kv head) to finish merges the splits (no separate combine launch)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tk = atomicAdd(&a.tickets[seq * a.nkv + g], 1);
+        s_last = (tk == nsplit_seq - 1);
+        if (s_last) a.tickets[seq * a.nkv + g] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int idx = threadIdx.x; idx < R * (HD / 4); idx += blockDim.x) {
+        const int r = idx / (HD / 4), d4 = idx - r * (HD / 4);
+        const int t = r / G, gq = r - t * G;
+        const size_t th = (size_t)(q0 + t) * a.nh + g * G + gq;
+        const int qpos = kv_len - qlen + t;
+        const int ns = min(nsplit_seq, qpos / a.split_keys + 1);   // splits that contain a visible key
+        const size_t base = th * a.nsplit_max;
+        float mx = -INFINITY;
+        for (int s2 = 0; s2 < ns; ++s2) mx = fmaxf(mx, __ldcg(&a.ml_part[(base + s2) * 2]));
+        float l = 0.0f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s2 = 0; s2 < ns; ++s2) {
+            const float w = exp2f(__ldcg(&a.ml_part[(base + s2) * 2]) - mx);
+            l += __ldcg(&a.ml_part[(base + s2) * 2 + 1]) * w;
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(a.o_part + (base + s2) * HD) + d4);
+            acc.x += v.x * w;
+            acc.y += v.y * w;
+            acc.z += v.z * w;
+            acc.w += v.w * w;
+        }
+        const float inv = 1.0f / l;
+        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(a.out + th * HD) + d4 * 2;
+        op[0] = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
+        op[1] = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
+    }
 }
 
 static int g_attn_attr = 0;
+
+template <int HD, int KW>
+static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
+    attn_mma_kernel<HD, KW><<<grid, threads, smem, stream>>>(a);
+    ASD_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     if (L.M <= 0) return 0;
@@ -327,8 +429,10 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     }
     const int G = L.nh / L.nkv;
     const int rows = L.max_qlen * G;
-    const int warps = (rows + 15) / 16;
-    if (warps > 8) return set_error("attention: q_len * group = %d rows exceeds 128; chunk the query", rows);
+    const int rg = (rows + 15) / 16;
+    if (rg > 8) return set_error("attention: q_len * group = %d rows exceeds 128; chunk the query", rows);
+    const int kg = rg == 1 ? 4 : (rg == 2 ? 2 : 1);
+    const int warps = rg * kg;
     AttnArgs a;
     a.q = L.q;
     a.k_cache = L.k_cache;
@@ -343,25 +447,38 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     a.page_size = L.page_size;
     a.split_keys = L.split_keys;
     a.nsplit_max = L.nsplit_max;
+    a.rg_count = rg;
+    a.kg_count = kg;
     a.scale_log2 = scale_log2;
     a.o_part = L.o_part;
     a.ml_part = L.ml_part;
-    const size_t smem = (size_t)warps * 16 * L.hd * 2 + 4 * (size_t)kKeyTile * L.hd * 2;
+    a.tickets = L.tickets;
+    a.out = L.out;
+    size_t smem = (size_t)rg * 16 * L.hd * 2 + 4 * (size_t)kKeyTile * L.hd * 2;
+    const size_t merge = (size_t)rg * 16 * L.hd * 2 + (size_t)warps * 16 * (L.hd + 2) * 4;
+    if (kg > 1 && merge > smem) smem = merge;
     if (!g_attn_attr) {
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         g_attn_attr = 1;
     }
     const dim3 grid(L.nseq, L.nkv, L.nsplit_max);
+    const int kw = kKeyTile / kg, th = warps * 32;
+    int rc;
     if (L.hd == 128)
-        attn_mma_kernel<128><<<grid, warps * 32, smem, stream>>>(a);
+        rc = kw == 64 ? launch_mma<128, 64>(a, grid, th, smem, stream)
+                      : (kw == 32 ? launch_mma<128, 32>(a, grid, th, smem, stream)
+                                  : launch_mma<128, 16>(a, grid, th, smem, stream));
     else
-        attn_mma_kernel<64><<<grid, warps * 32, smem, stream>>>(a);
-    ASD_CUDA(cudaGetLastError());
-    attn_combine_kernel<<<dim3(L.M, L.nh), 64, 0, stream>>>(L.o_part, L.ml_part, L.positions, L.split_keys,
-                                                           L.nsplit_max, L.hd, L.out, L.nh);
-    ASD_CUDA(cudaGetLastError());
-    count_launch(2);
+        rc = kw == 64 ? launch_mma<64, 64>(a, grid, th, smem, stream)
+                      : (kw == 32 ? launch_mma<64, 32>(a, grid, th, smem, stream)
+                                  : launch_mma<64, 16>(a, grid, th, smem, stream));
+    if (rc) return rc;
+    count_launch(1);
     return 0;
 }
 

@@ -49,12 +49,15 @@ struct Engine {
     int num_pages = 0, max_seqs = 0, max_pages = 0;
     // owned activations
     float *resid = nullptr, *part = nullptr, *o_part = nullptr, *ml_part = nullptr;
+    int* tickets = nullptr;
+    float2* rope_cs = nullptr;
     __nv_bfloat16 *xnorm = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *xsel = nullptr;
     size_t part_floats = 0, o_part_floats = 0;
     std::unordered_map<int, Plans> plans;
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     // options
-    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1;
+    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
+        attn_target_ctas = 296, fuse_rope = 1;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // profiling (option "profile"): CUDA-event pairs around every launch, by kernel class
@@ -96,7 +99,9 @@ static int ensure_plans(Engine* e, int M, Plans** out) {
     }
     Plans p;
     const int h = e->c.hidden;
-    if (gemm_plan(&p.qkv, M, e->nqkv, h, GEMM_OUT_F32, e->force_ksplit, e->force_stages, e->reduce)) return -1;
+    if (gemm_plan(&p.qkv, M, e->nqkv, h, (e->reduce && e->fuse_rope) ? GEMM_OUT_QKV : GEMM_OUT_F32, e->force_ksplit,
+                  e->force_stages, e->reduce))
+        return -1;
     if (gemm_plan(&p.o, M, h, e->qdim, GEMM_OUT_F32, e->force_ksplit, e->force_stages, e->reduce)) return -1;
     if (gemm_plan(&p.gu, M, 2 * e->ffp, h, GEMM_OUT_SWIGLU, 0, e->force_stages, 0)) return -1;
     if (gemm_plan(&p.down, M, h, e->c.ffn, GEMM_OUT_F32, e->force_ksplit, e->force_stages, e->reduce)) return -1;
@@ -134,8 +139,8 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     if (tp && !e->allreduce) return set_error("engine: tp_size > 1 but no all-reduce installed");
 
     // attention split selection: enough CTAs to fill the machine, bounded workspace
-    int nsplit = (2 * 148 + nseq * nkv - 1) / (nseq * nkv);
-    const int max_by_len = (max_kv_len + 63) / 64;
+    int nsplit = (e->attn_target_ctas + nseq * nkv - 1) / (nseq * nkv);
+    const int max_by_len = max_kv_len / 768 > 0 ? max_kv_len / 768 : 1;   // splitting only pays for long contexts
     if (nsplit > max_by_len) nsplit = max_by_len;
     if (nsplit > e->max_attn_splits) nsplit = e->max_attn_splits;
     if (nsplit < 1) nsplit = 1;
@@ -148,20 +153,39 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         PROF(PROF_GLUE);
         if (launch_add_norm(e->resid, nullptr, 0, 0, tokens, e->embed, e->layers[0].ln1, e->xnorm, M, h, c.rms_eps, s))
             return -1;
+        if (P->qkv.mode == GEMM_OUT_QKV && launch_rope_table(positions, e->inv_freq, e->rope_cs, M, hd / 2, s)) return -1;
     }
     for (int l = 0; l < c.n_layers; ++l) {
         Layer& L = e->layers[l];
         __nv_bfloat16* kc = e->kv_pool + (size_t)(2 * l) * e->kv_half;
         __nv_bfloat16* vc = kc + e->kv_half;
-        {
+        if (P->qkv.mode == GEMM_OUT_QKV) {   // bias + RoPE + q store + paged K/V append fused into the epilogue
             PROF(PROF_GEMM);
-            if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, e->part, e->nqkv, e->nqkv, e->pdl, s)) return -1;
-        }
-        {
-        PROF(PROF_GLUE);
-        if (launch_qkv_rope(e->part, P->qkv.reduce ? 1 : P->qkv.ksplit, (size_t)M * e->nqkv, L.bqkv, positions, token_slot, e->page_table,
-                            e->max_pages, e->inv_freq, e->q, kc, vc, M, nh, nkv, hd, c.page_size, s))
-            return -1;
+            QkvEpilogue q;
+            q.cs = e->rope_cs;
+            q.bias = L.bqkv;
+            q.positions = positions;
+            q.token_slot = token_slot;
+            q.page_table = e->page_table;
+            q.q_out = e->q;
+            q.k_cache = kc;
+            q.v_cache = vc;
+            q.max_pages = e->max_pages;
+            q.nh = nh;
+            q.nkv = nkv;
+            q.hd = hd;
+            q.page_size = c.page_size;
+            if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, nullptr, e->nqkv, e->nqkv, e->pdl, s, false, &q)) return -1;
+        } else {
+            {
+                PROF(PROF_GEMM);
+                if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, e->part, e->nqkv, e->nqkv, e->pdl, s)) return -1;
+            }
+            PROF(PROF_GLUE);
+            if (launch_qkv_rope(e->part, P->qkv.reduce ? 1 : P->qkv.ksplit, (size_t)M * e->nqkv, L.bqkv, positions,
+                                token_slot, e->page_table, e->max_pages, e->inv_freq, e->q, kc, vc, M, nh, nkv, hd,
+                                c.page_size, s))
+                return -1;
         }
         AttnLaunch A;
         A.q = e->q;
@@ -175,6 +199,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         A.out = e->attn;
         A.o_part = e->o_part;
         A.ml_part = e->ml_part;
+        A.tickets = e->tickets;
         A.M = M;
         A.nseq = nseq;
         A.max_qlen = max_qlen;
@@ -296,6 +321,9 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
     alloc((void**)&e->part, e->part_floats * 4);
     alloc((void**)&e->o_part, e->o_part_floats * 4);
     alloc((void**)&e->ml_part, Mx * c.n_heads * (size_t)e->max_attn_splits * 2 * 4);
+    alloc((void**)&e->rope_cs, Mx * (c.head_dim / 2) * sizeof(float2));
+    alloc((void**)&e->tickets, Mx * c.n_kv_heads * 4);
+    if (ok && cudaMemset(e->tickets, 0, Mx * c.n_kv_heads * 4) != cudaSuccess) ok = false;
     alloc((void**)&e->xnorm, Mx * c.hidden * 2);
     alloc((void**)&e->xsel, Mx * c.hidden * 2);
     alloc((void**)&e->q, Mx * e->qdim * 2);
@@ -311,7 +339,7 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
 void asd_engine_destroy(asd_engine_t* h) {
     Engine* e = reinterpret_cast<Engine*>(h);
     if (!e) return;
-    void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->xnorm, e->xsel, e->q, e->attn, e->act};
+    void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->tickets, e->rope_cs, e->xnorm, e->xsel, e->q, e->attn, e->act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete e;
@@ -382,6 +410,8 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "ksplit")) e->force_ksplit = value;
     else if (!strcmp(name, "stages")) e->force_stages = value;
     else if (!strcmp(name, "reduce")) e->reduce = value;
+    else if (!strcmp(name, "attn_target_ctas")) e->attn_target_ctas = value;
+    else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "profile")) {
         e->profile = value;
         e->ev_used.clear();

@@ -47,6 +47,7 @@ struct GemmArgs {
     uint32_t tmem_cols;
     int reduce;         // 1: the K splits of a tile form a cluster and reduce through DSMEM
     int accumulate;     // fp32 output is added to what is already there (fused residual add)
+    QkvEpilogue qkv;    // GEMM_OUT_QKV only
 };
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
@@ -89,36 +90,37 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp != 1) {
+        // ------------------------------------------------------------------ TMA producers
+        // One thread can only issue ~2 box copies per microsecond (measured: a single producer caps a
+        // CTA at ~34 GB/s whatever the ring depth), so lane 0 of warp 0 AND of the four epilogue warps
+        // (idle during the main loop) share the ring slots.
         if (lane == 0) {
+            // Each ring slot belongs to ONE producer (slot % nprod), so a producer is never more than one
+            // phase ahead of the slot's barriers (mbarrier parity waits are only unambiguous then).
+            const int pidx = warp == 0 ? 0 : warp - 1;   // 0..4
+            const int nprod = a.stages < 5 ? a.stages : 5;
             const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
-            // Weights do not depend on the upstream kernel: start streaming them before the
-            // programmatic-dependent-launch wait; activations only after it.
-            int pre = nkb < a.stages ? nkb : a.stages;
-            for (int kb = 0; kb < pre; ++kb) {
-                mbar_expect_tx(&full_bar[kb], stage_bytes);
-                tma_load_2d_hint(smem + (size_t)kb * stage_bytes, &tmap_w, (kb0 + kb) * kBlockK, tile_n * kTileN,
-                                 &full_bar[kb], pol_w);
-            }
-            grid_dep_wait();
-            for (int kb = 0; kb < pre; ++kb)
-                tma_load_2d_hint(smem + (size_t)kb * stage_bytes + kABytes, &tmap_x, (kb0 + kb) * kBlockK,
-                                 tile_m * a.MT, &full_bar[kb], pol_x);
-            int s = pre % a.stages;
-            uint32_t ph = (pre == a.stages) ? 1 : 0;  // parity of the NEXT use of slot s
-            for (int kb = pre; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
+            bool waited = false;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % a.stages, round = kb / a.stages;
+                if (s % nprod != pidx) continue;
+                if (round > 0) mbar_wait(&empty_bar[s], (round & 1) ^ 1);
                 mbar_expect_tx(&full_bar[s], stage_bytes);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
+                // weights do not depend on the upstream kernel: issue them before the PDL wait
                 tma_load_2d_hint(st, &tmap_w, (kb0 + kb) * kBlockK, tile_n * kTileN, &full_bar[s], pol_w);
-                tma_load_2d_hint(st + kABytes, &tmap_x, (kb0 + kb) * kBlockK, tile_m * a.MT, &full_bar[s], pol_x);
-                if (++s == a.stages) {
-                    s = 0;
-                    ph ^= 1;
+                if (!waited) {
+                    grid_dep_wait();
+                    waited = true;
                 }
+                tma_load_2d_hint(st + kABytes, &tmap_x, (kb0 + kb) * kBlockK, tile_m * a.MT, &full_bar[s], pol_x);
             }
         }
+        __syncwarp();
+    }
+    if (warp == 0) {
+        // nothing else to do until teardown
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_bf16(kTileN, a.MT);
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         const int m0 = tile_m * a.MT;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        grid_dep_wait();     // (already satisfied) makes the upstream grid's writes to `out` visible here
         grid_dep_launch();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         if (a.reduce) {
@@ -232,9 +235,21 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         cluster_sync();
         // receive layout in the owner: recv[src][col][lrow] (lrow contiguous) so that the 32 lanes of a
         // warp (32 consecutive accumulator rows) write contiguous 64-128 byte runs through DSMEM
+        // QKV mode keeps the two halves of every rotary pair in the same owner: within a head, pair p
+        // (dims p and p + hd/2) goes to owner p / pp, pp = (hd/2) / ks pairs per owner per head.
+        const bool qkv = a.mode == GEMM_OUT_QKV;
+        const int hd = qkv ? a.qkv.hd : kTileN, half = hd >> 1, pp = half / ks;
         if (warp >= 2) {
             const int q = warp & 3, row = q * 32 + lane;
-            const int owner = row / rows_per, lrow = row - owner * rows_per;
+            int owner, lrow;
+            if (qkv) {
+                const int h2 = row / hd, within = row - h2 * hd, hi = within / half, pr = within - hi * half;
+                owner = pr / pp;
+                lrow = (h2 * 2 + hi) * pp + (pr - owner * pp);
+            } else {
+                owner = row / rows_per;
+                lrow = row - owner * rows_per;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t dst = mapa(smem_u32(smem) + (uint32_t)((int)my_rank * a.MT * rows_per + lrow) * 4u,
                                       (uint32_t)owner);
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
             tc_fence_before();
         }
         cluster_sync();
-        if (warp >= 2) {
+        if (warp >= 2 && !qkv) {
             const int et = threadIdx.x - 64;
             const int first = (int)my_rank * rows_per;
             const int nrows = min(rows_per, kTileN - first);
@@ -265,6 +280,47 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
                     float* o = out + (size_t)m * a.ldo + n;
                     *o = a.accumulate ? *o + acc : acc;
                 }
+            }
+        } else if (warp >= 2) {
+            // bias + RoPE + q store / paged K,V append for this owner's pairs (all heads of the tile)
+            const int et = threadIdx.x - 64;
+            const float* recv = reinterpret_cast<const float*>(smem);
+            const QkvEpilogue& e = a.qkv;
+            const int heads_per_tile = kTileN / hd, m0 = tile_m * a.MT;
+            const int per_col = heads_per_tile * pp;                 // pairs of one token in this CTA
+            for (int idx = et; idx < per_col * a.MT; idx += 128) {
+                const int col = idx / per_col, rem = idx - col * per_col;
+                const int h2 = rem / pp, pq = rem - h2 * pp;
+                const int m = m0 + col;
+                const int head = tile_n * heads_per_tile + h2;       // q heads, then k heads, then v heads
+                if (m >= a.M || head >= e.nh + 2 * e.nkv) continue;
+                const int l1 = (h2 * 2) * pp + pq, l2 = (h2 * 2 + 1) * pp + pq;
+                float x1 = recv[col * rows_per + l1], x2 = recv[col * rows_per + l2];
+                for (int src = 1; src < ks; ++src) {
+                    x1 += recv[(src * a.MT + col) * rows_per + l1];
+                    x2 += recv[(src * a.MT + col) * rows_per + l2];
+                }
+                const int i = (int)my_rank * pp + pq;                // dim index of the pair, 0 .. hd/2
+                x1 += __bfloat162float(e.bias[head * hd + i]);
+                x2 += __bfloat162float(e.bias[head * hd + i + half]);
+                float o1 = x1, o2 = x2;
+                if (head < e.nh + e.nkv) {
+                    const float2 cs = e.cs[(size_t)m * half + i];
+                    o1 = x1 * cs.x - x2 * cs.y;
+                    o2 = x2 * cs.x + x1 * cs.y;
+                }
+                __nv_bfloat16* dstp;
+                if (head < e.nh) {
+                    dstp = e.q_out + ((size_t)m * e.nh + head) * hd;
+                } else {
+                    const int pos = e.positions[m];
+                    const int page = e.page_table[(size_t)e.token_slot[m] * e.max_pages + pos / e.page_size];
+                    const int g = head < e.nh + e.nkv ? head - e.nh : head - e.nh - e.nkv;
+                    __nv_bfloat16* cache = head < e.nh + e.nkv ? e.k_cache : e.v_cache;
+                    dstp = cache + (((size_t)page * e.nkv + g) * e.page_size + pos % e.page_size) * hd;
+                }
+                dstp[i] = __float2bfloat16(o1);
+                dstp[i + half] = __float2bfloat16(o2);
             }
         }
     }
@@ -333,7 +389,7 @@ int gemm_token_tile(int M) {
 // Choose the split so that all CTAs fit in one co-resident wave and there are enough bytes in flight.
 int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages, int reduce) {
     if (device_props()) return -1;
-    pl->reduce = (reduce && mode == GEMM_OUT_F32) ? 1 : 0;
+    pl->reduce = ((reduce && mode == GEMM_OUT_F32) || mode == GEMM_OUT_QKV) ? 1 : 0;
     if (M <= 0 || N <= 0 || K <= 0 || (K & 7)) return set_error("gemm: need M, N, K > 0 and K %% 8 == 0");
     pl->M = M;
     pl->N = N;
@@ -345,32 +401,39 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     pl->kblocks = (K + kBlockK - 1) / kBlockK;
     const int stage_bytes = kABytes + pl->MT * 128;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + (mode == GEMM_OUT_SWIGLU ? 2 * 64 * 33 * 4 : 0);
-    // residency target: 3 CTAs/SM for small token tiles, 2 for large ones
-    const int ctas_per_sm = pl->MT <= 128 ? 3 : 2;
-    const int budget = (227 * 1024) / ctas_per_sm - fixed - 1024;
-    int stages = budget / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    const int slots = g_num_sms * ctas_per_sm;
+    const int max_ctas_per_sm = pl->MT <= 128 ? 3 : 2;   // TMEM: 128 / 256 columns per CTA
     const int tiles = pl->n_tiles * pl->m_tiles;
+    // Split choice.  Measured on B200: one SM cannot ingest more than ~40 GB/s from HBM however deep its
+    // pipeline is, so a weight stream reaches HBM speed only if all 148 SMs carry the same number of
+    // bytes.  Pick the split that minimises the heaviest SM's load  ceil(CTAs / SMs) * kblocks / ksplit
+    // while every CTA stays co-resident (one wave) and keeps >= 4 k-blocks of work.
     int ksplit = 1;
     if (mode != GEMM_OUT_SWIGLU && mode != GEMM_OUT_BF16) {
-        // largest split that keeps every CTA resident, each with >= 4 k-blocks of work; with the
-        // in-cluster reduction the split is bounded by the portable cluster size (8)
+        // largest split that keeps every CTA co-resident in one wave with >= 4 k-blocks each; with the
+        // in-cluster reduction it is a power of two <= 8 (cluster sizes that tile the GPCs evenly)
+        const int slots = g_num_sms * max_ctas_per_sm;
         ksplit = slots / tiles;
         if (ksplit < 1) ksplit = 1;
         const int max_by_k = pl->kblocks / 4 > 0 ? pl->kblocks / 4 : 1;
         if (ksplit > max_by_k) ksplit = max_by_k;
         if (ksplit > (pl->reduce ? 8 : 16)) ksplit = pl->reduce ? 8 : 16;
-        if (pl->reduce) {  // cluster sizes that tile the GPCs evenly: 1, 2, 4, 8
+        if (pl->reduce) {
             int p2 = 1;
             while (p2 * 2 <= ksplit) p2 *= 2;
             ksplit = p2;
         }
     }
     if (force_ksplit > 0) ksplit = force_ksplit;
+    // pipeline depth from the expected residency: fewer CTAs per SM -> deeper ring per CTA
+    int ctas_per_sm = (tiles * ksplit + g_num_sms - 1) / g_num_sms;
+    if (ctas_per_sm > max_ctas_per_sm) ctas_per_sm = max_ctas_per_sm;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const int budget = (225 * 1024) / ctas_per_sm - fixed - 1024;
+    int stages = budget / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
     if (force_stages > 0) stages = force_stages;
-    if (pl->reduce && ksplit > 1) {
+    if (pl->reduce && (ksplit > 1 || mode == GEMM_OUT_QKV)) {
         if (ksplit > 8) return set_error("gemm: cluster reduction supports ksplit <= 8");
         const int rows_per = (kTileN + ksplit - 1) / ksplit;
         const int recv = ksplit * rows_per * pl->MT * 4;
@@ -381,7 +444,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     if (ksplit > pl->kblocks) ksplit = pl->kblocks;
     pl->ksplit = ksplit;
     pl->stages = stages;
-    if (ksplit == 1) pl->reduce = 0;
+    if (ksplit == 1 && mode != GEMM_OUT_QKV) pl->reduce = 0;
     pl->smem_bytes = fixed + stages * stage_bytes;
     if (pl->smem_bytes > g_smem_optin) return set_error("gemm: tile does not fit in shared memory");
     uint32_t cols = 32;
@@ -391,7 +454,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
 }
 
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
-                int n_valid, bool pdl, cudaStream_t stream, bool accumulate) {
+                int n_valid, bool pdl, cudaStream_t stream, bool accumulate, const QkvEpilogue* qkv) {
     if (!g_gemm_attr_set) {
         if (device_props()) return -1;
         ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
@@ -412,6 +475,13 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.tmem_cols = pl.tmem_cols;
     a.reduce = pl.reduce;
     a.accumulate = accumulate ? 1 : 0;
+    a.qkv = QkvEpilogue{};
+    if (pl.mode == GEMM_OUT_QKV) {
+        if (!qkv) return set_error("gemm: QKV epilogue needs its operands");
+        a.qkv = *qkv;
+        const int half = qkv->hd / 2;
+        if ((qkv->hd != 64 && qkv->hd != 128) || half % pl.ksplit) return set_error("gemm: QKV epilogue shape");
+    }
     if (accumulate && pl.mode != GEMM_OUT_F32) return set_error("gemm: accumulate needs the fp32 epilogue");
     if (accumulate && pl.ksplit > 1 && !pl.reduce) return set_error("gemm: accumulate needs the cluster reduction");
     cudaLaunchConfig_t cfg = {};

@@ -6,7 +6,20 @@
 
 namespace asd {
 
-enum GemmOut { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_SWIGLU = 2 };
+enum GemmOut { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_SWIGLU = 2, GEMM_OUT_QKV = 3 };
+
+// extra operands of the fused QKV epilogue (bias + rotate-half RoPE + q store + paged K/V append)
+struct QkvEpilogue {
+    const float2* cs;               // [M, hd/2] (cos, sin) of each token's position
+    const __nv_bfloat16* bias;      // [(nh + 2 nkv) * hd]
+    const int* positions;           // [M]
+    const int* token_slot;          // [M]
+    const int* page_table;          // [slots, max_pages]
+    __nv_bfloat16* q_out;           // [M, nh, hd]
+    __nv_bfloat16* k_cache;
+    __nv_bfloat16* v_cache;
+    int max_pages, nh, nkv, hd, page_size;
+};
 
 struct GemmPlan {
     int M, N, K, mode;
@@ -23,6 +36,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // out: GEMM_OUT_F32 -> float [ksplit][M][ldo]; GEMM_OUT_BF16 -> bf16 [M][ldo];
 // GEMM_OUT_SWIGLU -> bf16 [M][ldo] with N/2 columns (n_valid = ff)
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
-                int n_valid, bool pdl, cudaStream_t stream, bool accumulate = false);
+                int n_valid, bool pdl, cudaStream_t stream, bool accumulate = false,
+                const QkvEpilogue* qkv = nullptr);
 
 }  // namespace asd

@@ -193,6 +193,26 @@ int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const _
     return 0;
 }
 
+// (cos, sin) of every token's rotary angles, once per forward (consumed by the fused QKV epilogue)
+__global__ void rope_table_kernel(const int* __restrict__ positions, const float* __restrict__ inv_freq,
+                                  float2* __restrict__ cs, int half) {
+    const int m = blockIdx.x;
+    const float pos = (float)positions[m];
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float s, c;
+        sincosf(pos * inv_freq[i], &s, &c);
+        cs[(size_t)m * half + i] = make_float2(c, s);
+    }
+}
+
+int launch_rope_table(const int* positions, const float* inv_freq, float2* cs, int M, int half, cudaStream_t stream) {
+    if (M <= 0) return 0;
+    rope_table_kernel<<<M, 64, 0, stream>>>(positions, inv_freq, cs, half);
+    ASD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ rows,
                                    __nv_bfloat16* __restrict__ dst, int h) {
     const int r = blockIdx.x, sr = rows[r];

@@ -14,6 +14,7 @@ int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const _
                     const int* positions, const int* token_slot, const int* page_table, int max_pages,
                     const float* inv_freq, __nv_bfloat16* q_out, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int M,
                     int nh, int nkv, int hd, int page_size, cudaStream_t stream);
+int launch_rope_table(const int* positions, const float* inv_freq, float2* cs, int M, int half, cudaStream_t stream);
 int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16* dst, int n, int h,
                        cudaStream_t stream);
 
@@ -29,6 +30,7 @@ struct AttnLaunch {
     __nv_bfloat16* out;     // [M, nh, hd]
     float* o_part;
     float* ml_part;
+    int* tickets;           // [nseq * nkv] zero-initialised, self-resetting
     int M, nseq, max_qlen, nh, nkv, hd, page_size, max_pages, split_keys, nsplit_max, impl;
 };
 int launch_attention(const AttnLaunch& L, cudaStream_t stream);

@@ -244,6 +244,7 @@ def run_ours(args):
                          "bytes_per_forward": layer_bytes + head_bytes, "ms_per_forward": gemm_ms + head_ms},
             "verify_step_us": verify_ms * 1e3, "draft_step_us": draft_ms * 1e3,
             "verify_breakdown_ms": {c: round(v[0] / ps, 4) for c, v in prof_t.items()},
+            "draft_breakdown_ms": {c: round(v[0] / ps / max(k, 1), 4) for c, v in prof_d.items()},
             "step_hbm_frac": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -114,3 +114,14 @@ def bench_reduce():
 
 if len(sys.argv) > 1 and sys.argv[1] == "reduce":
     bench_reduce()
+
+
+def bench_auto():
+    for M, N, K, mode in [(96, 7168, 5120, 3), (96, 5120, 5120, 3), (96, 55296, 5120, 2), (96, 5120, 27648, 3),
+                          (16, 4608, 3584, 3), (16, 3584, 3584, 3), (16, 37888, 3584, 2), (16, 3584, 18944, 3),
+                          (16, 3584, 256, 3), (96, 5120, 256, 3)]:
+        bench_gemm(M, N, K, mode)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "auto":
+    bench_auto()
