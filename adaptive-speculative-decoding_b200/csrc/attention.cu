@@ -113,7 +113,8 @@ struct AttnArgs {
 
 // HD = head_dim (64 or 128); KW = keys of each 64-key tile handled by one warp (64, 32 or 16).
 // warp w = (row group w % rg_count, key group w / rg_count): 16 query rows x KW keys per tile.
-template <int HD, int KW>
+// NS = depth of the cp.async K/V ring (4 when there is one CTA per SM, 2 otherwise).
+template <int HD, int KW, int NS>
 __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     constexpr int CH = HD / 8;          // 16-byte chunks per row
     constexpr int ROWB = HD * 2;        // bytes per row
@@ -124,12 +125,13 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rg = warp % a.rg_count, kg = warp / a.rg_count;
     uint8_t* sQ = smem_raw;                                   // [rg_count*16][HD]
-    uint8_t* sK = sQ + (size_t)a.rg_count * 16 * ROWB;        // [2][64][HD]
-    uint8_t* sV = sK + 2 * kKeyTile * ROWB;                   // [2][64][HD]
+    uint8_t* sK = sQ + (size_t)a.rg_count * 16 * ROWB;        // [NS][64][HD]
+    uint8_t* sV = sK + NS * kKeyTile * ROWB;                  // [NS][64][HD]
     const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
 
     const int seq = blockIdx.x, g = blockIdx.y, sp = blockIdx.z;
     const int G = a.nh / a.nkv;
+    grid_dep_wait();   // q and the new K/V come from the QKV GEMM launched just before
     const int q0 = a.cu_q[seq], qlen = a.cu_q[seq + 1] - q0;
     if (qlen <= 0) return;
     const int R = qlen * G;
@@ -150,23 +152,32 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
         const __nv_bfloat16* src = a.q + ((size_t)(q0 + t) * a.nh + g * G + gq) * HD + ch * 8;
         cp_async16(uQ + r * ROWB + ((ch ^ (r & 7)) << 4), src, ok);
     }
+    // 4 threads per key row: one page-table lookup per (thread, row), then CH/4 16-byte chunks of K and V
     auto load_tile = [&](int tile, int buf) {
         const int j0 = kbeg + tile * kKeyTile;
-        for (int c = threadIdx.x; c < kKeyTile * CH; c += blockDim.x) {
-            const int r = c / CH, ch = c - r * CH;
+        const int sub = threadIdx.x & 3;
+        for (int r = threadIdx.x >> 2; r < kKeyTile; r += blockDim.x >> 2) {
             const int j = j0 + r;
             const bool ok = j < kend;
             const int jj = ok ? j : kbeg;
             const int page = pt[jj / a.page_size];
-            const size_t off = (((size_t)page * a.nkv + g) * a.page_size + jj % a.page_size) * HD + ch * 8;
-            const uint32_t d = (uint32_t)(buf * kKeyTile * ROWB + r * ROWB + ((ch ^ (r & 7)) << 4));
-            cp_async16(uK + d, a.k_cache + off, ok);
-            cp_async16(uV + d, a.v_cache + off, ok);
+            const size_t off = (((size_t)page * a.nkv + g) * a.page_size + jj % a.page_size) * HD;
+            const uint32_t drow = (uint32_t)(buf * kKeyTile * ROWB + r * ROWB);
+#pragma unroll
+            for (int cc = 0; cc < CH / 4; ++cc) {
+                const int ch = sub * (CH / 4) + cc;
+                const uint32_t d = drow + ((ch ^ (r & 7)) << 4);
+                cp_async16(uK + d, a.k_cache + off + ch * 8, ok);
+                cp_async16(uV + d, a.v_cache + off + ch * 8, ok);
+            }
         }
     };
     const int ntiles = (kend - kbeg + kKeyTile - 1) / kKeyTile;
-    load_tile(0, 0);
-    cp_async_commit();
+#pragma unroll
+    for (int t = 0; t < NS - 1; ++t) {   // prologue: NS-1 tiles in flight (Q rides in the first group)
+        if (t < ntiles) load_tile(t, t);
+        cp_async_commit();
+    }
 
     const int r0 = rg * 16 + (lane >> 2), r1 = r0 + 8;
     const int qpos0 = kv_len - qlen + (r0 < R ? r0 / G : 0), qpos1 = kv_len - qlen + (r1 < R ? r1 / G : 0);
@@ -177,10 +188,10 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     uint32_t qf[KB][4];
 
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int buf = tile & 1;
-        if (tile + 1 < ntiles) load_tile(tile + 1, buf ^ 1);
+        const int buf = tile % NS;
+        if (tile + NS - 1 < ntiles) load_tile(tile + NS - 1, (tile + NS - 1) % NS);
         cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<NS - 1>();
         __syncthreads();
         if (tile == 0) {
             const int mi = lane >> 3;
@@ -406,12 +417,25 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     }
 }
 
-static int g_attn_attr = 0;
-
-template <int HD, int KW>
+template <int HD, int KW, int NS>
 static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
-    attn_mma_kernel<HD, KW><<<grid, threads, smem, stream>>>(a);
-    ASD_CUDA(cudaGetLastError());
+    static bool attr_set = false;
+    if (!attr_set) {
+        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<HD, KW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_glue_pdl ? 1 : 0;
+    ASD_CUDA(cudaLaunchKernelEx(&cfg, attn_mma_kernel<HD, KW, NS>, a));
     return 0;
 }
 
@@ -454,29 +478,20 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     a.ml_part = L.ml_part;
     a.tickets = L.tickets;
     a.out = L.out;
-    size_t smem = (size_t)rg * 16 * L.hd * 2 + 4 * (size_t)kKeyTile * L.hd * 2;
+    const dim3 grid(L.nseq, L.nkv, L.nsplit_max);
+    const int ns = (int)(grid.x * grid.y * grid.z) <= 148 ? 4 : 2;   // one CTA per SM: deeper K/V ring
+    size_t smem = (size_t)rg * 16 * L.hd * 2 + 2 * (size_t)ns * kKeyTile * L.hd * 2;
     const size_t merge = (size_t)rg * 16 * L.hd * 2 + (size_t)warps * 16 * (L.hd + 2) * 4;
     if (kg > 1 && merge > smem) smem = merge;
-    if (!g_attn_attr) {
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        g_attn_attr = 1;
-    }
-    const dim3 grid(L.nseq, L.nkv, L.nsplit_max);
     const int kw = kKeyTile / kg, th = warps * 32;
     int rc;
+#define ASD_ATTN(HD_, KW_) (ns == 4 ? launch_mma<HD_, KW_, 4>(a, grid, th, smem, stream) \
+                                    : launch_mma<HD_, KW_, 2>(a, grid, th, smem, stream))
     if (L.hd == 128)
-        rc = kw == 64 ? launch_mma<128, 64>(a, grid, th, smem, stream)
-                      : (kw == 32 ? launch_mma<128, 32>(a, grid, th, smem, stream)
-                                  : launch_mma<128, 16>(a, grid, th, smem, stream));
+        rc = kw == 64 ? ASD_ATTN(128, 64) : (kw == 32 ? ASD_ATTN(128, 32) : ASD_ATTN(128, 16));
     else
-        rc = kw == 64 ? launch_mma<64, 64>(a, grid, th, smem, stream)
-                      : (kw == 32 ? launch_mma<64, 32>(a, grid, th, smem, stream)
-                                  : launch_mma<64, 16>(a, grid, th, smem, stream));
+        rc = kw == 64 ? ASD_ATTN(64, 64) : (kw == 32 ? ASD_ATTN(64, 32) : ASD_ATTN(64, 16));
+#undef ASD_ATTN
     if (rc) return rc;
     count_launch(1);
     return 0;

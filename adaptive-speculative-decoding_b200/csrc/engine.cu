@@ -57,7 +57,7 @@ struct Engine {
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     // options
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
-        attn_target_ctas = 296, fuse_rope = 1;
+        attn_target_ctas = 148, fuse_rope = 1;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // profiling (option "profile"): CUDA-event pairs around every launch, by kernel class
@@ -139,8 +139,8 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     if (tp && !e->allreduce) return set_error("engine: tp_size > 1 but no all-reduce installed");
 
     // attention split selection: enough CTAs to fill the machine, bounded workspace
-    int nsplit = (e->attn_target_ctas + nseq * nkv - 1) / (nseq * nkv);
-    const int max_by_len = max_kv_len / 768 > 0 ? max_kv_len / 768 : 1;   // splitting only pays for long contexts
+    int nsplit = (e->attn_target_ctas + nseq * nkv / 2) / (nseq * nkv);   // rounded: fill the SMs once
+    const int max_by_len = max_kv_len / 256 > 0 ? max_kv_len / 256 : 1;   // >= 4 key tiles per split
     if (nsplit > max_by_len) nsplit = max_by_len;
     if (nsplit > e->max_attn_splits) nsplit = e->max_attn_splits;
     if (nsplit < 1) nsplit = 1;
@@ -412,6 +412,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "reduce")) e->reduce = value;
     else if (!strcmp(name, "attn_target_ctas")) e->attn_target_ctas = value;
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
+    else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
     else if (!strcmp(name, "profile")) {
         e->profile = value;
         e->ev_used.clear();

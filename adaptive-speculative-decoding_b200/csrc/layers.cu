@@ -16,6 +16,8 @@
 
 namespace asd {
 
+int g_glue_pdl = 1;   // launch the glue kernels programmatically (they wait on griddepcontrol)
+
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxVec = 8;  // float4 per thread -> hidden <= 8192
 
@@ -39,6 +41,7 @@ __global__ void __launch_bounds__(kNormThreads) add_norm_kernel(float* __restric
                                                                  const __nv_bfloat16* __restrict__ w,
                                                                  __nv_bfloat16* __restrict__ xnorm, int h, float eps) {
     __shared__ float scratch[kNormThreads / 32];
+    grid_dep_wait();    // launched programmatically: the upstream kernel's results are needed from here on
     grid_dep_launch();  // lets the next GEMM start streaming its weights (it waits before reading x)
     const int m = blockIdx.x, nvec = h >> 2;
     float4 v[kNormMaxVec];
@@ -92,8 +95,16 @@ int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_s
                     cudaStream_t stream) {
     if (h % 4 || h > kNormThreads * kNormMaxVec * 4) return set_error("add_norm: hidden must be %%4 and <= 8192");
     if (M <= 0) return 0;
-    add_norm_kernel<<<M, kNormThreads, 0, stream>>>(resid, part, nslices, slice_stride, tokens, emb, w, xnorm, h, eps);
-    ASD_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(M);
+    cfg.blockDim = dim3(kNormThreads);
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_glue_pdl ? 1 : 0;
+    ASD_CUDA(cudaLaunchKernelEx(&cfg, add_norm_kernel, resid, part, nslices, slice_stride, tokens, emb, w, xnorm, h, eps));
     count_launch(1);
     return 0;
 }

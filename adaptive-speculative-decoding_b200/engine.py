@@ -199,6 +199,8 @@ class SpecDecoder:
         self.last_tok = torch.zeros(batch, dtype=torch.int32, device=dev)
         self.prev_tok = torch.zeros(batch, dtype=torch.int32, device=dev)
         self.kv_bound = 0     # host-side upper bound of every sequence length (no sync needed)
+        self.time_verify = False
+        self.verify_events = []
         self._empty_i = torch.zeros(batch, 0, dtype=torch.int32, device=dev)
         self._empty_d = torch.zeros(batch, 0, dtype=torch.float64, device=dev)
 
@@ -250,7 +252,13 @@ class SpecDecoder:
             toks = torch.cat([self.last_tok[:, None], self.draft_tokens], 1)
         else:
             toks = self.last_tok[:, None]
+        if self.time_verify:     # two CUDA events per step on the launching stream (bench.py)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         self.t.forward_uniform(toks, self.pos, self.slots, bound, logits_out=self.target_logits)
+        if self.time_verify:
+            ev[1].record()
+            self.verify_events.append(ev)
         out = self.sampler(self.target_logits, self.draft_logits if k > 0 and self.T > 0 else None,
                            self.draft_tokens[:, :k].contiguous() if k > 0 else self._empty_i,
                            self._uniform(B, k) if k > 0 else self._empty_d, self._uniform(B), self.T)

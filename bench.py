@@ -165,12 +165,16 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     emitted = torch.zeros((), dtype=torch.int64, device=dev)
     barrier()
+    dec.time_verify, dec.verify_events = True, []
     ev[0].record()
     for _ in range(args.steps):
         out = dec.step()
         emitted += (out["accepted_len"].to(torch.int64) + 1).sum()
     ev[1].record()
     barrier()
+    dec.time_verify = False
+    verify_ms_timed = sorted(a.elapsed_time(b) for a, b in dec.verify_events)
+    verify_ms_timed = verify_ms_timed[len(verify_ms_timed) // 2]
     launches = int(L.asd_launch_count())
     ms_total = ev[0].elapsed_time(ev[1])
     tokens = int(emitted.item())
@@ -242,7 +246,9 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "bytes_per_forward": layer_bytes + head_bytes, "ms_per_forward": gemm_ms + head_ms},
-            "verify_step_us": verify_ms * 1e3, "draft_step_us": draft_ms * 1e3,
+            "verify_step_us": verify_ms_timed * 1e3, "draft_step_us": draft_ms * 1e3,
+            "verify_step_hbm_frac": (tcfg.streamed_bytes() / world + kv_bytes) / (verify_ms_timed * 1e-3) / 1e9 / peak,
+            "verify_step_us_profiled": verify_ms * 1e3,
             "verify_breakdown_ms": {c: round(v[0] / ps, 4) for c, v in prof_t.items()},
             "draft_breakdown_ms": {c: round(v[0] / ps / max(k, 1), 4) for c, v in prof_d.items()},
             "step_hbm_frac": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak,
