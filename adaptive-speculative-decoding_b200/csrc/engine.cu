@@ -51,13 +51,15 @@ struct Engine {
     float *resid = nullptr, *part = nullptr, *o_part = nullptr, *ml_part = nullptr;
     int* tickets = nullptr;
     float2* rope_cs = nullptr;
+    __nv_bfloat16* resid_bf = nullptr;
+    float *sumsq = nullptr, *sumsq_sel = nullptr;
     __nv_bfloat16 *xnorm = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *xsel = nullptr;
     size_t part_floats = 0, o_part_floats = 0;
     std::unordered_map<int, Plans> plans;
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     // options
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
-        attn_target_ctas = 148, fuse_rope = 1;
+        attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // profiling (option "profile"): CUDA-event pairs around every launch, by kernel class
@@ -108,7 +110,7 @@ static int ensure_plans(Engine* e, int M, Plans** out) {
     const size_t need = (size_t)M * std::max(std::max((size_t)p.qkv.ksplit * e->nqkv, (size_t)p.o.ksplit * h),
                                              (size_t)p.down.ksplit * h);
     if (need > e->part_floats) return set_error("engine: split-K workspace too small for M = %d", M);
-    if (make_tmap_bf16(&p.x_norm, e->xnorm, M, h, h, p.qkv.MT)) return -1;
+    if (make_tmap_bf16(&p.x_norm, e->fuse_norm ? e->resid_bf : e->xnorm, M, h, h, p.qkv.MT)) return -1;
     if (make_tmap_bf16(&p.x_attn, e->attn, M, e->qdim, e->qdim, p.o.MT)) return -1;
     if (make_tmap_bf16(&p.x_act, e->act, M, e->c.ffn, e->c.ffn, p.down.MT)) return -1;
     auto r = e->plans.emplace(M, p);
@@ -132,15 +134,17 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     if (!e->embed || !e->kv_pool || !e->inv_freq) return set_error("engine: weights / KV pool not set");
     for (auto& L : e->layers)
         if (!L.wqkv) return set_error("engine: a layer has no weights");
+    const bool fn = e->fuse_norm != 0;   // RMSNorm folded into the consumer GEMMs (weights must be pre-folded)
+    if (fn && !(e->reduce && e->fuse_rope)) return set_error("engine: fuse_norm needs reduce = 1 and fuse_rope = 1");
     Plans* P = nullptr;
     if (ensure_plans(e, M, &P)) return -1;
-    const int h = c.hidden, nh = c.n_heads, nkv = c.n_kv_heads, hd = c.head_dim;
+    const int h = c.hidden, nh = c.n_heads, nkv = c.n_kv_heads, hd = c.head_dim, Mx = c.max_tokens;
     const bool tp = c.tp_size > 1;
     if (tp && !e->allreduce) return set_error("engine: tp_size > 1 but no all-reduce installed");
 
-    // attention split selection: enough CTAs to fill the machine, bounded workspace
-    int nsplit = (e->attn_target_ctas + nseq * nkv / 2) / (nseq * nkv);   // rounded: fill the SMs once
-    const int max_by_len = max_kv_len / 256 > 0 ? max_kv_len / 256 : 1;   // >= 4 key tiles per split
+    // attention split selection: fill the SMs once, >= 4 key tiles per split, bounded workspace
+    int nsplit = (e->attn_target_ctas + nseq * nkv / 2) / (nseq * nkv);
+    const int max_by_len = max_kv_len / 256 > 0 ? max_kv_len / 256 : 1;
     if (nsplit > max_by_len) nsplit = max_by_len;
     if (nsplit > e->max_attn_splits) nsplit = e->max_attn_splits;
     if (nsplit < 1) nsplit = 1;
@@ -149,12 +153,58 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     const int nsplit_max = (max_kv_len + split_keys - 1) / split_keys;
     if ((size_t)M * nh * nsplit_max * hd > e->o_part_floats) return set_error("engine: attention workspace too small");
 
+    int parts = 1;   // rows of e->sumsq that currently describe the residual (fused-norm mode)
+    NormFusion cons;  // consumer-side descriptor, refreshed before each consumer GEMM
+    auto consumer = [&](const float* ss) -> const NormFusion* {
+        if (!fn) return nullptr;
+        cons = NormFusion{};
+        cons.sumsq_in = ss;
+        cons.parts = parts;
+        cons.ld = Mx;
+        cons.hidden = h;
+        cons.eps = c.rms_eps;
+        return &cons;
+    };
     {
         PROF(PROF_GLUE);
-        if (launch_add_norm(e->resid, nullptr, 0, 0, tokens, e->embed, e->layers[0].ln1, e->xnorm, M, h, c.rms_eps, s))
+        if (launch_add_norm(e->resid, nullptr, 0, 0, tokens, e->embed, e->layers[0].ln1, fn ? nullptr : e->xnorm, M, h,
+                            c.rms_eps, s, fn ? e->resid_bf : nullptr, fn ? e->sumsq : nullptr))
             return -1;
         if (P->qkv.mode == GEMM_OUT_QKV && launch_rope_table(positions, e->inv_freq, e->rope_cs, M, hd / 2, s)) return -1;
     }
+    // residual update after a row-parallel projection: fused into the GEMM when possible, else glue kernel
+    auto project_residual = [&](const GemmPlan& pl, const CUtensorMap& tw, const CUtensorMap& tx,
+                                const __nv_bfloat16* next_ln) -> int {
+        const bool fuse = !tp && (pl.reduce || pl.ksplit == 1);
+        const bool emit = fn && fuse && pl.reduce && pl.ksplit >= 4;
+        NormFusion prod;
+        if (emit) {
+            prod.sumsq_out = e->sumsq;
+            prod.ld = Mx;
+            prod.resid_bf = e->resid_bf;
+        }
+        {
+            PROF(PROF_GEMM);
+            if (gemm_launch(pl, tw, tx, fuse ? (void*)e->resid : (void*)e->part, h, h, e->pdl, s, fuse, nullptr,
+                            emit ? &prod : nullptr))
+                return -1;
+        }
+        if (emit) {
+            parts = pl.n_tiles;
+            return 0;
+        }
+        int ns = fuse ? 0 : (pl.reduce ? 1 : pl.ksplit);
+        if (tp) {
+            PROF(PROF_COMM);
+            if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
+            ns = 1;
+        }
+        PROF(PROF_GLUE);
+        parts = 1;
+        return launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, next_ln,
+                               fn ? nullptr : (next_ln ? e->xnorm : nullptr), M, h, c.rms_eps, s,
+                               fn ? e->resid_bf : nullptr, fn ? e->sumsq : nullptr);
+    };
     for (int l = 0; l < c.n_layers; ++l) {
         Layer& L = e->layers[l];
         __nv_bfloat16* kc = e->kv_pool + (size_t)(2 * l) * e->kv_half;
@@ -175,7 +225,9 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             q.nkv = nkv;
             q.hd = hd;
             q.page_size = c.page_size;
-            if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, nullptr, e->nqkv, e->nqkv, e->pdl, s, false, &q)) return -1;
+            if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, nullptr, e->nqkv, e->nqkv, e->pdl, s, false, &q,
+                            consumer(e->sumsq)))
+                return -1;
         } else {
             {
                 PROF(PROF_GEMM);
@@ -215,58 +267,30 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             PROF(PROF_ATTN);
             if (launch_attention(A, s)) return -1;
         }
-        // fused residual add: with the in-cluster reduction the GEMM accumulates straight into resid
-        const bool fuse_o = !tp && (P->o.reduce || P->o.ksplit == 1);
+        if (project_residual(P->o, L.t_o, P->x_attn, L.ln2)) return -1;
         {
             PROF(PROF_GEMM);
-            if (gemm_launch(P->o, L.t_o, P->x_attn, fuse_o ? (void*)e->resid : (void*)e->part, h, h, e->pdl, s, fuse_o))
+            if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s, false, nullptr,
+                            consumer(e->sumsq)))
                 return -1;
         }
-        int ns = fuse_o ? 0 : (P->o.reduce ? 1 : P->o.ksplit);
-        if (tp) {
-            PROF(PROF_COMM);
-            if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
-            ns = 1;
-        }
-        {
-            PROF(PROF_GLUE);
-            if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, L.ln2, e->xnorm, M, h,
-                                c.rms_eps, s))
-                return -1;
-        }
-        {
-            PROF(PROF_GEMM);
-            if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s)) return -1;
-        }
-        const bool fuse_d = !tp && (P->down.reduce || P->down.ksplit == 1);
-        {
-            PROF(PROF_GEMM);
-            if (gemm_launch(P->down, L.t_down, P->x_act, fuse_d ? (void*)e->resid : (void*)e->part, h, h, e->pdl, s,
-                            fuse_d))
-                return -1;
-        }
-        ns = fuse_d ? 0 : (P->down.reduce ? 1 : P->down.ksplit);
-        if (tp) {
-            PROF(PROF_COMM);
-            if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
-            ns = 1;
-        }
-        PROF(PROF_GLUE);
-        const __nv_bfloat16* wn = (l + 1 < c.n_layers) ? e->layers[l + 1].ln1 : e->final_norm;
         const bool last = l + 1 == c.n_layers;
-        if (launch_add_norm(e->resid, e->part, ns, (size_t)M * h, nullptr, nullptr, wn,
-                            (last && n_logit_rows == 0) ? nullptr : e->xnorm, M, h, c.rms_eps, s))
-            return -1;
+        const __nv_bfloat16* wn = last ? e->final_norm : e->layers[l + 1].ln1;
+        if (project_residual(P->down, L.t_down, P->x_act, (last && n_logit_rows == 0 && !fn) ? nullptr : wn)) return -1;
     }
     if (n_logit_rows <= 0) return 0;
     if (!logits_out) return set_error("engine: logits_out is NULL");
     int rows = M;
-    const __nv_bfloat16* src = e->xnorm;
+    const __nv_bfloat16* src = fn ? e->resid_bf : e->xnorm;
+    const float* ss = e->sumsq;
     int key = M;
     if (logit_rows) {
-        if (launch_gather_rows(e->xnorm, logit_rows, e->xsel, n_logit_rows, h, s)) return -1;
+        if (launch_gather_rows(src, logit_rows, e->xsel, n_logit_rows, h, s, fn ? e->sumsq : nullptr, e->sumsq_sel, parts,
+                               Mx))
+            return -1;
         rows = n_logit_rows;
         src = e->xsel;
+        ss = e->sumsq_sel;
         key = -rows;
     } else if (n_logit_rows != M) {
         return set_error("engine: n_logit_rows must equal M when logit_rows is NULL");
@@ -280,7 +304,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     }
     PROF(PROF_LMHEAD);
     return gemm_launch(it->second.first, e->t_lm, it->second.second, logits_out,
-                       logits_ld > 0 ? (int)logits_ld : c.vocab, c.vocab, e->pdl, s);
+                       logits_ld > 0 ? (int)logits_ld : c.vocab, c.vocab, e->pdl, s, false, nullptr, consumer(ss));
 }
 
 }  // namespace asd
@@ -322,6 +346,9 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
     alloc((void**)&e->o_part, e->o_part_floats * 4);
     alloc((void**)&e->ml_part, Mx * c.n_heads * (size_t)e->max_attn_splits * 2 * 4);
     alloc((void**)&e->rope_cs, Mx * (c.head_dim / 2) * sizeof(float2));
+    alloc((void**)&e->resid_bf, Mx * c.hidden * 2);
+    alloc((void**)&e->sumsq, Mx * (size_t)((c.hidden + 127) / 128) * 4);
+    alloc((void**)&e->sumsq_sel, Mx * (size_t)((c.hidden + 127) / 128) * 4);
     alloc((void**)&e->tickets, Mx * c.n_kv_heads * 4);
     if (ok && cudaMemset(e->tickets, 0, Mx * c.n_kv_heads * 4) != cudaSuccess) ok = false;
     alloc((void**)&e->xnorm, Mx * c.hidden * 2);
@@ -339,7 +366,8 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
 void asd_engine_destroy(asd_engine_t* h) {
     Engine* e = reinterpret_cast<Engine*>(h);
     if (!e) return;
-    void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->tickets, e->rope_cs, e->xnorm, e->xsel, e->q, e->attn, e->act};
+    void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->tickets, e->rope_cs, e->resid_bf, e->sumsq,
+                    e->sumsq_sel, e->xnorm, e->xsel, e->q, e->attn, e->act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete e;
@@ -413,6 +441,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "attn_target_ctas")) e->attn_target_ctas = value;
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
+    else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
     else if (!strcmp(name, "profile")) {
         e->profile = value;
         e->ev_used.clear();

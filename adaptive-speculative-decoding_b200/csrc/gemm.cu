@@ -48,6 +48,7 @@ struct GemmArgs {
     int reduce;         // 1: the K splits of a tile form a cluster and reduce through DSMEM
     int accumulate;     // fp32 output is added to what is already there (fused residual add)
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
+    NormFusion norm;
 };
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
@@ -63,7 +64,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
     uint64_t* empty_bar = full_bar + a.stages;
     uint64_t* tmem_full = empty_bar + a.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* xbuf = reinterpret_cast<float*>(tmem_slot + 4);  // SwiGLU exchange: [2][64][33] floats
+    uint64_t* rstd_bar = reinterpret_cast<uint64_t*>(tmem_slot + 4);
+    float* rstd_s = reinterpret_cast<float*>(rstd_bar + 1);   // [MT] per-token rstd (fused RMSNorm consumer)
+    float* xbuf = rstd_s + a.MT;  // SwiGLU exchange [2][64][33] floats / sum-of-squares exchange [256 + ks*MT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_n = blockIdx.x, split = blockIdx.y, tile_m = blockIdx.z;
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
+        mbar_init(rstd_bar, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -90,16 +94,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp != 1) {
+    if (warp >= 2) {
         // ------------------------------------------------------------------ TMA producers
-        // One thread can only issue ~2 box copies per microsecond (measured: a single producer caps a
-        // CTA at ~34 GB/s whatever the ring depth), so lane 0 of warp 0 AND of the four epilogue warps
-        // (idle during the main loop) share the ring slots.
+        // Lane 0 of each of the four epilogue warps (idle during the main loop) owns the ring slots
+        // s with s % nprod == its index, so a producer is never more than one phase ahead of a slot's
+        // barriers (mbarrier parity waits are only unambiguous then).
         if (lane == 0) {
-            // Each ring slot belongs to ONE producer (slot % nprod), so a producer is never more than one
-            // phase ahead of the slot's barriers (mbarrier parity waits are only unambiguous then).
-            const int pidx = warp == 0 ? 0 : warp - 1;   // 0..4
-            const int nprod = a.stages < 5 ? a.stages : 5;
+            const int pidx = warp - 2;   // 0..3
+            const int nprod = a.stages < 4 ? a.stages : 4;
             const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
             bool waited = false;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -120,7 +122,19 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         __syncwarp();
     }
     if (warp == 0) {
-        // nothing else to do until teardown
+        // ------------------------------------------------------------------ fused RMSNorm: per-token rstd
+        if (a.norm.sumsq_in != nullptr) {
+            grid_dep_wait();
+            for (int c = lane; c < a.MT; c += 32) {
+                const int m = tile_m * a.MT + c;
+                float ssum = 0.0f;
+                if (m < a.M)
+                    for (int t = 0; t < a.norm.parts; ++t) ssum += a.norm.sumsq_in[(size_t)t * a.norm.ld + m];
+                rstd_s[c] = rsqrtf(ssum / (float)a.norm.hidden + a.norm.eps);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rstd_bar);
+        }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_bf16(kTileN, a.MT);
@@ -154,6 +168,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         tc_fence_after();
         grid_dep_wait();     // (already satisfied) makes the upstream grid's writes to `out` visible here
         grid_dep_launch();
+        const bool scale = a.norm.sumsq_in != nullptr;
+        if (scale) mbar_wait(rstd_bar, 0);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         if (a.reduce) {
             // handled below by the whole cluster
@@ -182,8 +198,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int m = m0 + c0 + ch + i;
-                    if (c0 + ch + i < a.MT && m < a.M && j < a.n_valid)
-                        out[(size_t)m * a.ldo + j] = __float2bfloat16(silu_mul(g[i], u[i]));
+                    if (c0 + ch + i < a.MT && m < a.M && j < a.n_valid) {
+                        const float rs = scale ? rstd_s[c0 + ch + i] : 1.0f;
+                        out[(size_t)m * a.ldo + j] = __float2bfloat16(silu_mul(g[i] * rs, u[i] * rs));
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -213,7 +231,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
                             const int m = m0 + c0 + i;
                             if (c0 + i < a.MT && m < a.M) {
                                 float* o = out + (size_t)m * a.ldo + n;
-                                *o = a.accumulate ? *o + __uint_as_float(r[i]) : __uint_as_float(r[i]);
+                                const float v = scale ? __uint_as_float(r[i]) * rstd_s[c0 + i] : __uint_as_float(r[i]);
+                                *o = a.accumulate ? *o + v : v;
                             }
                         }
                     }
@@ -271,16 +290,48 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
             const float* recv = reinterpret_cast<const float*>(smem);
             float* out = static_cast<float*>(a.out);
             const int m0 = tile_m * a.MT;
+            const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees rows_per <= 32 in this mode
+            float* colsum = xbuf;                            // [MT] this owner's sum of squares per token
             for (int idx = et; idx < rows_per * a.MT; idx += 128) {
                 const int col = idx / rows_per, lrow = idx - col * rows_per;
                 float acc = recv[idx];
                 for (int src = 1; src < ks; ++src) acc += recv[src * a.MT * rows_per + idx];
                 const int n = tile_n * kTileN + first + lrow, m = m0 + col;
+                float sq = 0.0f;
                 if (lrow < nrows && m < a.M && n < a.n_valid) {
                     float* o = out + (size_t)m * a.ldo + n;
-                    *o = a.accumulate ? *o + acc : acc;
+                    const float v = a.accumulate ? *o + acc : acc;
+                    *o = v;
+                    if (emit) {
+                        a.norm.resid_bf[(size_t)m * a.ldo + n] = __float2bfloat16(v);
+                        sq = v * v;
+                    }
+                }
+                if (emit) {   // the rows_per lanes that share this column are consecutive: tree-reduce them
+                    for (int d = rows_per >> 1; d >= 1; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+                    if (lrow == 0) colsum[col] = sq;
                 }
             }
+            if (emit) {
+                // owners -> rank 0 (DSMEM), rank 0 adds the ks values in rank order and publishes the tile's row
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t g0 = mapa(smem_u32(xbuf + 256 + (int)my_rank * a.MT), 0);
+                for (int c = et; c < a.MT; c += 128) st_cluster_f32(g0 + c * 4, colsum[c]);
+            }
+        }
+        if (a.norm.sumsq_out != nullptr && !qkv) {
+            cluster_sync();
+            if (warp >= 2 && my_rank == 0) {
+                const int et = threadIdx.x - 64, m0 = tile_m * a.MT;
+                for (int c = et; c < a.MT; c += 128) {
+                    float t = 0.0f;
+                    for (int r2 = 0; r2 < ks; ++r2) t += xbuf[256 + r2 * a.MT + c];
+                    if (m0 + c < a.M) a.norm.sumsq_out[(size_t)tile_n * a.norm.ld + m0 + c] = t;
+                }
+            }
+        }
+        if (!qkv) {
+            // fp32 modes were handled above
         } else if (warp >= 2) {
             // bias + RoPE + q store / paged K,V append for this owner's pairs (all heads of the tile)
             const int et = threadIdx.x - 64;
@@ -301,6 +352,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
                     x2 += recv[(src * a.MT + col) * rows_per + l2];
                 }
                 const int i = (int)my_rank * pp + pq;                // dim index of the pair, 0 .. hd/2
+                if (a.norm.sumsq_in != nullptr) {
+                    x1 *= rstd_s[col];
+                    x2 *= rstd_s[col];
+                }
                 x1 += __bfloat162float(e.bias[head * hd + i]);
                 x2 += __bfloat162float(e.bias[head * hd + i + half]);
                 float o1 = x1, o2 = x2;
@@ -400,7 +455,8 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     pl->n_tiles = (N + kTileN - 1) / kTileN;
     pl->kblocks = (K + kBlockK - 1) / kBlockK;
     const int stage_bytes = kABytes + pl->MT * 128;
-    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + (mode == GEMM_OUT_SWIGLU ? 2 * 64 * 33 * 4 : 0);
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + pl->MT * 4 /*rstd*/ +
+                      (mode == GEMM_OUT_SWIGLU ? 2 * 64 * 33 * 4 : (mode == GEMM_OUT_F32 ? (256 + 8 * pl->MT) * 4 : 0));
     const int max_ctas_per_sm = pl->MT <= 128 ? 3 : 2;   // TMEM: 128 / 256 columns per CTA
     const int tiles = pl->n_tiles * pl->m_tiles;
     // Split choice.  Measured on B200: one SM cannot ingest more than ~40 GB/s from HBM however deep its
@@ -454,7 +510,8 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
 }
 
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
-                int n_valid, bool pdl, cudaStream_t stream, bool accumulate, const QkvEpilogue* qkv) {
+                int n_valid, bool pdl, cudaStream_t stream, bool accumulate, const QkvEpilogue* qkv,
+                const NormFusion* norm) {
     if (!g_gemm_attr_set) {
         if (device_props()) return -1;
         ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
@@ -475,6 +532,12 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.tmem_cols = pl.tmem_cols;
     a.reduce = pl.reduce;
     a.accumulate = accumulate ? 1 : 0;
+    a.norm = norm ? *norm : NormFusion{};
+    if (a.norm.sumsq_out != nullptr) {
+        if (!pl.reduce || pl.ksplit < 4 || pl.mode != GEMM_OUT_F32)
+            return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction with ksplit >= 4");
+        if (!a.norm.resid_bf) return set_error("gemm: fused norm producer needs resid_bf");
+    }
     a.qkv = QkvEpilogue{};
     if (pl.mode == GEMM_OUT_QKV) {
         if (!qkv) return set_error("gemm: QKV epilogue needs its operands");

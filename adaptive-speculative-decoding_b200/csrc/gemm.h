@@ -8,6 +8,17 @@ namespace asd {
 
 enum GemmOut { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_SWIGLU = 2, GEMM_OUT_QKV = 3 };
 
+// Fused RMSNorm.  Consumer side: x is the UN-normalised bf16 residual, the ln weight is folded into W, and the
+// epilogue scales token m by rstd[m] = rsqrt(sum_t sumsq[t][m] / hidden + eps).  Producer side (fp32
+// accumulate epilogue): besides the fp32 residual it writes the bf16 copy and this tile's sum of squares.
+struct NormFusion {
+    const float* sumsq_in = nullptr;   // consumer: [parts][ld]
+    int parts = 0, ld = 0, hidden = 0;
+    float eps = 0.f;
+    float* sumsq_out = nullptr;        // producer: [n_tiles][ld]
+    __nv_bfloat16* resid_bf = nullptr; // producer: [M][ldo] bf16 copy of the updated residual
+};
+
 // extra operands of the fused QKV epilogue (bias + rotate-half RoPE + q store + paged K/V append)
 struct QkvEpilogue {
     const float2* cs;               // [M, hd/2] (cos, sin) of each token's position
@@ -37,6 +48,6 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // GEMM_OUT_SWIGLU -> bf16 [M][ldo] with N/2 columns (n_valid = ff)
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
                 int n_valid, bool pdl, cudaStream_t stream, bool accumulate = false,
-                const QkvEpilogue* qkv = nullptr);
+                const QkvEpilogue* qkv = nullptr, const NormFusion* norm = nullptr);
 
 }  // namespace asd

@@ -39,7 +39,9 @@ __global__ void __launch_bounds__(kNormThreads) add_norm_kernel(float* __restric
                                                                  const int* __restrict__ tokens,
                                                                  const __nv_bfloat16* __restrict__ emb,
                                                                  const __nv_bfloat16* __restrict__ w,
-                                                                 __nv_bfloat16* __restrict__ xnorm, int h, float eps) {
+                                                                 __nv_bfloat16* __restrict__ xnorm, int h, float eps,
+                                                                 __nv_bfloat16* __restrict__ resid_bf,
+                                                                 float* __restrict__ sumsq0) {
     __shared__ float scratch[kNormThreads / 32];
     grid_dep_wait();    // launched programmatically: the upstream kernel's results are needed from here on
     grid_dep_launch();  // lets the next GEMM start streaming its weights (it waits before reading x)
@@ -73,6 +75,18 @@ __global__ void __launch_bounds__(kNormThreads) add_norm_kernel(float* __restric
         }
     }
     const float tot = block_sum(ss, scratch);
+    if (resid_bf != nullptr) {   // fused-norm mode: the consumer GEMM normalises; publish bf16(resid) and sum x^2
+#pragma unroll
+        for (int i = 0; i < kNormMaxVec; ++i) {
+            const int c = threadIdx.x + i * kNormThreads;
+            if (c < nvec) {
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(resid_bf + (size_t)m * h) + 2 * c;
+                op[0] = __floats2bfloat162_rn(v[i].x, v[i].y);
+                op[1] = __floats2bfloat162_rn(v[i].z, v[i].w);
+            }
+        }
+        if (threadIdx.x == 0) sumsq0[m] = tot;
+    }
     const float inv = rsqrtf(tot / (float)h + eps);
     if (xnorm == nullptr) return;
 #pragma unroll
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(kNormThreads) add_norm_kernel(float* __restric
 
 int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_stride, const int* tokens,
                     const __nv_bfloat16* emb, const __nv_bfloat16* w, __nv_bfloat16* xnorm, int M, int h, float eps,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, __nv_bfloat16* resid_bf, float* sumsq0) {
     if (h % 4 || h > kNormThreads * kNormMaxVec * 4) return set_error("add_norm: hidden must be %%4 and <= 8192");
     if (M <= 0) return 0;
     cudaLaunchConfig_t cfg = {};
@@ -104,7 +118,8 @@ int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_s
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = g_glue_pdl ? 1 : 0;
-    ASD_CUDA(cudaLaunchKernelEx(&cfg, add_norm_kernel, resid, part, nslices, slice_stride, tokens, emb, w, xnorm, h, eps));
+    ASD_CUDA(cudaLaunchKernelEx(&cfg, add_norm_kernel, resid, part, nslices, slice_stride, tokens, emb, w, xnorm, h, eps,
+                                resid_bf, sumsq0));
     count_launch(1);
     return 0;
 }
@@ -225,17 +240,20 @@ int launch_rope_table(const int* positions, const float* inv_freq, float2* cs, i
 }
 
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ rows,
-                                   __nv_bfloat16* __restrict__ dst, int h) {
+                                   __nv_bfloat16* __restrict__ dst, int h, const float* __restrict__ ss_src,
+                                   float* __restrict__ ss_dst, int parts, int ld) {
     const int r = blockIdx.x, sr = rows[r];
+    if (ss_src != nullptr)
+        for (int t = threadIdx.x; t < parts; t += blockDim.x) ss_dst[(size_t)t * ld + r] = ss_src[(size_t)t * ld + sr];
     const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)sr * h);
     uint4* d = reinterpret_cast<uint4*>(dst + (size_t)r * h);
     for (int i = threadIdx.x; i < h / 8; i += blockDim.x) d[i] = s[i];
 }
 
 int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16* dst, int n, int h,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const float* ss_src, float* ss_dst, int parts, int ld) {
     if (n <= 0) return 0;
-    gather_rows_kernel<<<n, 128, 0, stream>>>(src, rows, dst, h);
+    gather_rows_kernel<<<n, 128, 0, stream>>>(src, rows, dst, h, ss_src, ss_dst, parts, ld);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

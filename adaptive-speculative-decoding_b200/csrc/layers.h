@@ -10,7 +10,7 @@ extern int g_glue_pdl;
 
 int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_stride, const int* tokens,
                     const __nv_bfloat16* emb, const __nv_bfloat16* w, __nv_bfloat16* xnorm, int M, int h, float eps,
-                    cudaStream_t stream);
+                    cudaStream_t stream, __nv_bfloat16* resid_bf = nullptr, float* sumsq0 = nullptr);
 int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream);
 int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const __nv_bfloat16* bias,
                     const int* positions, const int* token_slot, const int* page_table, int max_pages,
@@ -18,7 +18,8 @@ int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const _
                     int nh, int nkv, int hd, int page_size, cudaStream_t stream);
 int launch_rope_table(const int* positions, const float* inv_freq, float2* cs, int M, int half, cudaStream_t stream);
 int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16* dst, int n, int h,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const float* ss_src = nullptr, float* ss_dst = nullptr, int parts = 0,
+                       int ld = 0);
 
 struct AttnLaunch {
     const __nv_bfloat16* q;

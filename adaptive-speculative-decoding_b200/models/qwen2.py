@@ -104,9 +104,12 @@ def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor
 
 
 def pack_layer(w: Dict[str, torch.Tensor], cfg: Qwen2Config, l: int, tp_rank: int = 0, tp_size: int = 1,
-               device="cuda") -> Dict[str, torch.Tensor]:
+               device="cuda", fold_norm: bool = False) -> Dict[str, torch.Tensor]:
     """One layer of HF-named weights -> engine layout for one tensor-parallel rank (Megatron split:
-    heads and ffn columns are sharded, O / down are sharded along their input dimension)."""
+    heads and ffn columns are sharded, O / down are sharded along their input dimension).
+    ``fold_norm``: multiply the RMSNorm weights into the columns of the projections that consume the
+    normalised activations (engine option fuse_norm: the GEMM then reads the raw bf16 residual and its
+    epilogue applies the per-token rstd)."""
     p = f"model.layers.{l}."
     nh, nkv, hd, ff = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.intermediate_size
     assert nh % tp_size == 0 and nkv % tp_size == 0 and ff % tp_size == 0
@@ -116,11 +119,17 @@ def pack_layer(w: Dict[str, torch.Tensor], cfg: Qwen2Config, l: int, tp_rank: in
     sl = lambda t, n: t[r * n:(r + 1) * n]
     wq, wk, wv = (w[p + f"self_attn.{n}_proj.weight"] for n in "qkv")
     bq, bk, bv = (w[p + f"self_attn.{n}_proj.bias"] for n in "qkv")
+    wg, wu = w[p + "mlp.gate_proj.weight"], w[p + "mlp.up_proj.weight"]
+    if fold_norm:
+        ln1 = w[p + "input_layernorm.weight"].float()[None, :]
+        ln2 = w[p + "post_attention_layernorm.weight"].float()[None, :]
+        wq, wk, wv = ((t.float() * ln1).to(torch.bfloat16) for t in (wq, wk, wv))
+        wg, wu = ((t.float() * ln2).to(torch.bfloat16) for t in (wg, wu))
     out = {
         "wqkv": dev(torch.cat([sl(wq, nhl * hd), sl(wk, nkvl * hd), sl(wv, nkvl * hd)], 0)),
         "bqkv": dev(torch.cat([sl(bq, nhl * hd), sl(bk, nkvl * hd), sl(bv, nkvl * hd)], 0)),
         "wo": dev(w[p + "self_attn.o_proj.weight"][:, r * nhl * hd:(r + 1) * nhl * hd]),
-        "wgateup": dev(interleave_gate_up(sl(w[p + "mlp.gate_proj.weight"], ffl), sl(w[p + "mlp.up_proj.weight"], ffl))),
+        "wgateup": dev(interleave_gate_up(sl(wg, ffl), sl(wu, ffl))),
         "wdown": dev(w[p + "mlp.down_proj.weight"][:, r * ffl:(r + 1) * ffl]),
         "ln1": dev(w[p + "input_layernorm.weight"]),
         "ln2": dev(w[p + "post_attention_layernorm.weight"]),

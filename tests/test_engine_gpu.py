@@ -14,12 +14,12 @@ pytestmark = pytest.mark.gpu
 MAX_ABS, ARGMAX = 2e-2, 0.999
 
 
-def run_engine(cfg, w, ids, q_verify, attn_impl, chunk=0, max_tokens=64):
+def run_engine(cfg, w, ids, q_verify, attn_impl, chunk=0, max_tokens=64, fuse_norm=True):
     """prefill the first T - q_verify tokens (chunked), then ONE verify-style forward of q_verify tokens
     per sequence; returns logits of the verify rows [B, q_verify, V] and of the last prefill row."""
     from asd_b200.engine import QwenEngine
     B, T = ids.shape
-    eng = QwenEngine(cfg, max_seqs=B + 1, max_seq_len=T + 16, max_tokens=max_tokens).load_hf_weights(w)
+    eng = QwenEngine(cfg, max_seqs=B + 1, max_seq_len=T + 16, max_tokens=max_tokens, fuse_norm=fuse_norm).load_hf_weights(w)
     eng.set_option("attn_impl", attn_impl)
     slots = torch.arange(1, B + 1, dtype=torch.int32, device="cuda")      # slot 0 deliberately unused
     P = T - q_verify
@@ -34,10 +34,15 @@ def run_engine(cfg, w, ids, q_verify, attn_impl, chunk=0, max_tokens=64):
 
 
 def check(got, ref):
+    """max-abs <= 2e-2; argmax agreement >= 99.9 %, where a disagreement only counts if it is not a near-tie
+    (the oracle's own margin between the two candidates must exceed twice the measured logit error)."""
     err = (got - ref).abs().max().item()
-    agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
     assert err <= MAX_ABS, err
-    assert agree >= ARGMAX, agree
+    ga, ra = got.argmax(-1), ref.argmax(-1)
+    margin = ref.gather(-1, ra[..., None])[..., 0] - ref.gather(-1, ga[..., None])[..., 0]
+    real_miss = (ga != ra) & (margin > 2 * err)
+    agree = 1.0 - real_miss.float().mean().item()
+    assert agree >= ARGMAX, (agree, err)
 
 
 @pytest.mark.parametrize("attn_impl", [0, 1])
@@ -54,6 +59,26 @@ def test_engine_logits_vs_oracle(name, cfg, B, T, q, attn_impl):
     ver, last = run_engine(cfg, w, ids, q, attn_impl)
     check(ver, ref[:, T - q:])
     check(last, ref[:, T - q - 1])
+
+
+@pytest.mark.parametrize("opts", [dict(fuse_norm=False), dict(fuse_norm=False, fuse_rope=0), dict(fuse_norm=False, reduce=0)])
+def test_engine_unfused_paths(opts):
+    """the glue-kernel paths (separate add+RMSNorm, separate RoPE kernel, fp32 K-split slices) stay correct"""
+    from asd_b200.engine import QwenEngine
+    cfg = Qwen2Config(512, 2, 10, 2, 1024, 4096, head_dim=128, name="g5")
+    w = random_hf_weights(cfg, seed=11)
+    ids = torch.randint(0, cfg.vocab_size, (3, 90), generator=torch.Generator().manual_seed(5))
+    ref = qwen2_forward(w, cfg, ids)
+    eng = QwenEngine(cfg, max_seqs=3, max_seq_len=128, max_tokens=64, fuse_norm=opts["fuse_norm"]).load_hf_weights(w)
+    for k_, v_ in opts.items():
+        if k_ != "fuse_norm":
+            eng.set_option(k_, v_)
+    slots = torch.arange(3, dtype=torch.int32, device="cuda")
+    idc = ids.cuda().to(torch.int32)
+    eng.prefill(idc[:, :84], slots)
+    ver = eng.forward_uniform(idc[:, 84:].contiguous(), torch.full((3,), 84, dtype=torch.int32, device="cuda"), slots, 90)
+    check(ver.view(3, 6, -1).cpu(), ref[:, 84:])
+    eng.close()
 
 
 def test_engine_hf_golden_weights():
