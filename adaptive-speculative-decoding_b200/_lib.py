@@ -44,6 +44,7 @@ def lib() -> ctypes.CDLL:
         "asd_launch_count": (c.c_longlong, []),
         "asd_reset_launch_count": (None, []),
         "asd_reject_sample_workspace_bytes": (sz, [i32, i32]),
+        "asd_reject_sample_set_impl": (None, [i32]),
         "asd_reject_sample": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
         "asd_reject_sample_host": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
         "asd_stop_rule": (i32, [vp, vp, i32, i32, f64, i32, f64, f64, vp, vp, vp]),

@@ -34,6 +34,7 @@ long long asd_launch_count(void) { return g_launches.load(); }
 void asd_reset_launch_count(void) { g_launches.store(0); }
 
 size_t asd_reject_sample_workspace_bytes(int B, int k) { return reject_sample_workspace_bytes(B, k); }
+void asd_reject_sample_set_impl(int impl) { g_sampler_impl = impl; }
 
 int asd_reject_sample(const float* target_logits, const float* draft_logits, const int32_t* draft_tokens,
                       const double* u_accept, const double* u_resid, int B, int k, int V, float temperature,

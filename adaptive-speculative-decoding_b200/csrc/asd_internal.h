@@ -25,6 +25,8 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
                          int* accepted_len, int* out_tokens, float* out_logprobs, float* features, void* workspace,
                          cudaStream_t stream);
 
+extern int g_sampler_impl;
+
 // stop_rule.cu
 int launch_stop_rule(const double* p, const double* C, int n, int L, double lam, int risk_adjustment, double alpha,
                      double beta, int* k_star, double* J, cudaStream_t stream);

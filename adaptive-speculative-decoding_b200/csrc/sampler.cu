@@ -161,6 +161,74 @@ __device__ __forceinline__ void cluster_scan(SmemCtl* ctl, int ex, uint32_t cran
     }
 }
 
+// Row epilogue executed by ONE thread of the cluster (rank 0, thread 0): accept test, features, per-row
+// scratch, and - for the last row of a sequence to finish - the first-reject prefix / emitted tokens.
+__device__ __noinline__ void row_epilogue(const SamplerParams& p, const SmemCtl* ctl, int row, int b, int i, int x,
+                                          bool x_ok, bool has_draft, int amax, float m1, float m2, float Zp, float Zq,
+                                          float Ssum, const float* zt) {
+    const float c1 = p.c1, nm1 = -m1;
+    const int k1 = p.k + 1;
+
+            const float ep_x = ctl->scal[0], eq_x = ctl->scal[1];
+            const bool has_y = ctl->scal[4] != 0.0f;
+            int y;
+            float ep_y;
+            int acc = 0;
+            if (p.greedy) {
+                y = amax;
+                acc = x_ok && x == y;
+                ep_y = exp2p(__fmaf_rn(zt[y], c1, nm1));
+            } else {
+                if (has_draft && x_ok) {
+                    const double lhs = __dmul_rn(__dmul_rn(p.u_accept[b * p.k + i], (double)eq_x), (double)Zp);
+                    const double rhs = __dmul_rn((double)ep_x, (double)Zq);
+                    acc = lhs <= rhs;
+                }
+                if (has_y) {
+                    y = __float_as_int(ctl->scal[3]);
+                    ep_y = ctl->scal[2];
+                } else {  // R == 0: p == q on this row
+                    y = x_ok ? x : 0;
+                    ep_y = x_ok ? ep_x : exp2p(__fmaf_rn(zt[0], c1, nm1));
+                }
+            }
+            const float logZ = logf(Zp), log2Z = log2f(Zp);
+            float* f = p.features + (size_t)row * kNFeat;
+            f[0] = __fmul_rn(__fadd_rn(m1, log2Z), 0x1.62e43p-1f);
+            f[1] = 1.0f / Zp;
+            f[2] = f[1] - exp2p(__fadd_rn(m2, nm1)) / Zp;
+            f[3] = (log2Z - Ssum / Zp) * 0x1.62e43p-1f;
+            f[4] = x_ok ? logf(ep_x) - logZ : -INFINITY;
+            f[5] = logf(ep_y) - logZ;
+            p.row_accept[row] = acc;
+            p.row_cand[row] = y;
+            p.row_lpx[row] = f[4];
+            p.row_lpy[row] = f[5];
+            __threadfence();
+            const int ticket = atomicAdd(&p.seq_counter[b], 1);
+            if (ticket == p.k) {  // last row of this sequence: first-reject prefix + emitted tokens
+                __threadfence();
+                int n = 0;
+                while (n < p.k && __ldcg(&p.row_accept[b * k1 + n])) ++n;
+                for (int t = 0; t < p.k; ++t) p.accept_mask[b * p.k + t] = t < n;
+                p.accepted_len[b] = n;
+                for (int t = 0; t < k1; ++t) {
+                    int tok = -1;
+                    float lp = 0.0f;
+                    if (t < n) {
+                        tok = p.draft_tokens[b * p.k + t];
+                        lp = __ldcg(&p.row_lpx[b * k1 + t]);
+                    } else if (t == n) {
+                        tok = __ldcg(&p.row_cand[b * k1 + t]);
+                        lp = __ldcg(&p.row_lpy[b * k1 + t]);
+                    }
+                    p.out_tokens[b * k1 + t] = tok;
+                    p.out_logprobs[b * k1 + t] = lp;
+                }
+                p.seq_counter[b] = 0;
+            }
+        }
+
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     reject_sample_kernel(const SamplerParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -378,74 +446,284 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         cluster_sync();
 
         // ------------------------------------------------------------ row epilogue (one thread)
-        if (crank == 0 && tid == 0) {
-            const float ep_x = ctl->scal[0], eq_x = ctl->scal[1];
-            const bool has_y = ctl->scal[4] != 0.0f;
-            int y;
-            float ep_y;
-            int acc = 0;
-            if (p.greedy) {
-                y = amax;
-                acc = x_ok && x == y;
-                ep_y = exp2p(__fmaf_rn(zt[y], c1, nm1));
-            } else {
-                if (has_draft && x_ok) {
-                    const double lhs = __dmul_rn(__dmul_rn(p.u_accept[b * p.k + i], (double)eq_x), (double)Zp);
-                    const double rhs = __dmul_rn((double)ep_x, (double)Zq);
-                    acc = lhs <= rhs;
-                }
-                if (has_y) {
-                    y = __float_as_int(ctl->scal[3]);
-                    ep_y = ctl->scal[2];
-                } else {  // R == 0: p == q on this row
-                    y = x_ok ? x : 0;
-                    ep_y = x_ok ? ep_x : exp2p(__fmaf_rn(zt[0], c1, nm1));
-                }
-            }
-            const float logZ = logf(Zp), log2Z = log2f(Zp);
-            float* f = p.features + (size_t)row * kNFeat;
-            f[0] = __fmul_rn(__fadd_rn(m1, log2Z), 0x1.62e43p-1f);
-            f[1] = 1.0f / Zp;
-            f[2] = f[1] - exp2p(__fadd_rn(m2, nm1)) / Zp;
-            f[3] = (log2Z - Ssum / Zp) * 0x1.62e43p-1f;
-            f[4] = x_ok ? logf(ep_x) - logZ : -INFINITY;
-            f[5] = logf(ep_y) - logZ;
-            p.row_accept[row] = acc;
-            p.row_cand[row] = y;
-            p.row_lpx[row] = f[4];
-            p.row_lpy[row] = f[5];
-            __threadfence();
-            const int ticket = atomicAdd(&p.seq_counter[b], 1);
-            if (ticket == p.k) {  // last row of this sequence: first-reject prefix + emitted tokens
-                __threadfence();
-                int n = 0;
-                while (n < p.k && __ldcg(&p.row_accept[b * k1 + n])) ++n;
-                for (int t = 0; t < p.k; ++t) p.accept_mask[b * p.k + t] = t < n;
-                p.accepted_len[b] = n;
-                for (int t = 0; t < k1; ++t) {
-                    int tok = -1;
-                    float lp = 0.0f;
-                    if (t < n) {
-                        tok = p.draft_tokens[b * p.k + t];
-                        lp = __ldcg(&p.row_lpx[b * k1 + t]);
-                    } else if (t == n) {
-                        tok = __ldcg(&p.row_cand[b * k1 + t]);
-                        lp = __ldcg(&p.row_lpy[b * k1 + t]);
-                    }
-                    p.out_tokens[b * k1 + t] = tok;
-                    p.out_logprobs[b * k1 + t] = lp;
-                }
-                p.seq_counter[b] = 0;
-            }
-        }
+        if (crank == 0 && tid == 0)
+            row_epilogue(p, ctl, row, b, i, x, x_ok, has_draft, amax, m1, m2, Zp, Zq, Ssum, zt);
         // CTA 0's leader must finish reading scal[] before any thread of the next row's pass 3
         // writes it: those writes happen after that row's cluster barriers, which the leader joins.
     }
     cluster_sync();
 }
 
-static int g_max_clusters[kMaxSlabs + 1];
-static int g_attr_set = 0;
+// ------------------------------------------------------------------------------------------------
+// Register-resident variant (V <= 10 slabs = 163840): identical arithmetic contract, different data
+// movement.  Shared memory is only a PREFETCH buffer: bulk TMA copies bring row r+1 in while row r is
+// processed out of registers (each thread keeps its NS float4 of the target and of the draft row), so the
+// HBM stream overlaps all three passes and no pass touches shared memory for data.  The polynomial
+// exp2 and the element-wise products run on the packed fp32x2 pipe (FFMA2 / FADD2 / FMUL2, sm_100):
+// each component is an IEEE fma/add/mul, so results are bit-identical to the scalar contract.
+__device__ __forceinline__ float2 exp2p2(float2 t) {
+    const float2 tc = make_float2(fmaxf(t.x, -125.0f), fmaxf(t.y, -125.0f));
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    const float2 r = __fadd2_rn(tc, magic);
+    const float2 nf = __fadd2_rn(r, nmagic);
+    const float2 f = __ffma2_rn(nf, make_float2(-1.0f, -1.0f), tc);   // tc - nf, exact
+    float2 q = make_float2(0x1.5c08e6p-10f, 0x1.5c08e6p-10f);
+    q = __ffma2_rn(q, f, make_float2(0x1.3d0c52p-7f, 0x1.3d0c52p-7f));
+    q = __ffma2_rn(q, f, make_float2(0x1.c6b6e4p-5f, 0x1.c6b6e4p-5f));
+    q = __ffma2_rn(q, f, make_float2(0x1.ebf918p-3f, 0x1.ebf918p-3f));
+    q = __ffma2_rn(q, f, make_float2(0x1.62e428p-1f, 0x1.62e428p-1f));
+    q = __ffma2_rn(q, f, make_float2(0x1.000002p+0f, 0x1.000002p+0f));
+    return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23)),
+                       __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23)));
+}
+
+template <int NS>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
+    reject_sample_reg_kernel(const SamplerParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float4* bufP = reinterpret_cast<float4*>(smem_raw);
+    float4* bufQ = bufP + NS * kThreads;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(bufQ + NS * kThreads);
+
+    const uint32_t crank = cluster_ctarank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cluster_id = blockIdx.x / kCluster, nclusters = gridDim.x / kCluster;
+    const int k1 = p.k + 1, rows = p.B * k1, V = p.V, nvec = V >> 2;
+    const float c1 = p.c1;
+    const float2 c1v = make_float2(c1, c1);
+
+    auto issue_row = [&](int row) {   // thread 0: bulk copies of this CTA's share of a row (pair) into smem
+        const int b = row / k1, i = row - b * k1;
+        const bool hd = (i < p.k) && !p.greedy;
+        const uint8_t* zt = reinterpret_cast<const uint8_t*>(p.target + (size_t)row * V);
+        const uint8_t* zq = hd ? reinterpret_cast<const uint8_t*>(p.draft + ((size_t)b * p.k + i) * V) : nullptr;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const long long off = (long long)s * kSlabVec * 16 + (long long)crank * kSlabBytesPerCta;
+            long long n = (long long)V * 4 - off;
+            n = n > kSlabBytesPerCta ? kSlabBytesPerCta : n;
+            if (n > 0) bytes += (uint32_t)n * (hd ? 2 : 1);
+        }
+        mbar_expect_tx(&ctl->bar, bytes);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const long long off = (long long)s * kSlabVec * 16 + (long long)crank * kSlabBytesPerCta;
+            long long n = (long long)V * 4 - off;
+            n = n > kSlabBytesPerCta ? kSlabBytesPerCta : n;
+            if (n > 0) {
+                bulk_g2s(bufP + s * kThreads, zt + off, (uint32_t)n, &ctl->bar);
+                if (hd) bulk_g2s(bufQ + s * kThreads, zq + off, (uint32_t)n, &ctl->bar);
+            }
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&ctl->bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    cluster_sync();
+    if (tid == 0 && cluster_id < rows) issue_row(cluster_id);
+
+    uint32_t phase = 0;
+    for (int row = cluster_id; row < rows; row += nclusters) {
+        const int b = row / k1, i = row - b * k1;
+        const bool has_draft = (i < p.k) && !p.greedy;
+        const float* zt_g = p.target + (size_t)row * V;
+
+        // ------------------------------------------------------------ smem -> registers, then prefetch the next row
+        mbar_wait(&ctl->bar, phase);
+        phase ^= 1;
+        float4 zt[NS], zq[NS];
+        bool have[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int j = s * kSlabVec + (int)crank * kThreads + tid;
+            have[s] = j < nvec;
+            zt[s] = have[s] ? bufP[s * kThreads + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+            zq[s] = (have[s] && has_draft) ? bufQ[s * kThreads + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tid == 0) ctl->scal[4] = 0.0f;
+        fence_proxy_async_smem();
+        __syncthreads();   // every thread has taken its data: the buffer is free for the next row
+        if (tid == 0 && row + nclusters < rows) issue_row(row + nclusters);
+
+        // ------------------------------------------------------------ pass 1: maxima
+        float m1 = -INFINITY, m2 = -INFINITY, mq = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (have[s]) {
+                const float2 a0 = __fmul2_rn(make_float2(zt[s].x, zt[s].y), c1v);
+                const float2 a1 = __fmul2_rn(make_float2(zt[s].z, zt[s].w), c1v);
+                const float a[4] = {a0.x, a0.y, a1.x, a1.y};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    m2 = fmaxf(m2, fminf(m1, a[e]));
+                    m1 = fmaxf(m1, a[e]);
+                }
+                if (has_draft) {
+                    const float2 q0 = __fmul2_rn(make_float2(zq[s].x, zq[s].y), c1v);
+                    const float2 q1 = __fmul2_rn(make_float2(zq[s].z, zq[s].w), c1v);
+                    mq = fmaxf(mq, fmaxf(fmaxf(q0.x, q0.y), fmaxf(q1.x, q1.y)));
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const float o1 = __shfl_xor_sync(0xffffffffu, m1, d), o2 = __shfl_xor_sync(0xffffffffu, m2, d);
+            m2 = fmaxf(fminf(m1, o1), fmaxf(m2, o2));
+            m1 = fmaxf(m1, o1);
+            mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, d));
+        }
+        if (lane == 0) {
+            ctl->warp_scratch[warp][0] = m1;
+            ctl->warp_scratch[warp][1] = m2;
+            ctl->warp_scratch[warp][2] = mq;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float v[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int w = 0; w < kWarps; ++w) {
+                const float o1 = ctl->warp_scratch[w][0], o2 = ctl->warp_scratch[w][1];
+                v[1] = fmaxf(fminf(v[0], o1), fmaxf(v[1], o2));
+                v[0] = fmaxf(v[0], o1);
+                v[2] = fmaxf(v[2], ctl->warp_scratch[w][2]);
+            }
+            xchg_publish(ctl, 0, crank, v, 3);
+        }
+        cluster_sync();
+        m1 = m2 = mq = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kCluster; ++c) {
+            const float o1 = ctl->xchg[0][c][0], o2 = ctl->xchg[0][c][1];
+            m2 = fmaxf(fminf(m1, o1), fmaxf(m2, o2));
+            m1 = fmaxf(m1, o1);
+            mq = fmaxf(mq, ctl->xchg[0][c][2]);
+        }
+
+        // ------------------------------------------------------------ pass 2: e = 2^(a - m) in registers, sums
+        float sums[3] = {0.0f, 0.0f, 0.0f};
+        int amax = 0x7fffffff;
+        const float nm1 = -m1, nmq = -mq;
+        const float2 nm1v = make_float2(nm1, nm1), nmqv = make_float2(nmq, nmq);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (have[s]) {
+                const int j = s * kSlabVec + (int)crank * kThreads + tid;
+                if (p.greedy) {
+                    const float zz[4] = {zt[s].x, zt[s].y, zt[s].z, zt[s].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (__fmul_rn(zz[e], c1) == m1) amax = min(amax, j * 4 + e);
+                }
+                const float2 t0 = __ffma2_rn(make_float2(zt[s].x, zt[s].y), c1v, nm1v);
+                const float2 t1 = __ffma2_rn(make_float2(zt[s].z, zt[s].w), c1v, nm1v);
+                const float2 e0 = exp2p2(t0), e1 = exp2p2(t1);
+                const float2 w0 = __fmul2_rn(e0, t0), w1 = __fmul2_rn(e1, t1);
+                sums[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sums[0], e0.x), e0.y), e1.x), e1.y);
+                sums[1] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sums[1], w0.x), w0.y), w1.x), w1.y);
+                zt[s] = make_float4(e0.x, e0.y, e1.x, e1.y);
+                if (has_draft) {
+                    const float2 q0 = exp2p2(__ffma2_rn(make_float2(zq[s].x, zq[s].y), c1v, nmqv));
+                    const float2 q1 = exp2p2(__ffma2_rn(make_float2(zq[s].z, zq[s].w), c1v, nmqv));
+                    sums[2] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sums[2], q0.x), q0.y), q1.x), q1.y);
+                    zq[s] = make_float4(q0.x, q0.y, q1.x, q1.y);
+                }
+            }
+        }
+        float Pz[3], Xz[3], tot[3];
+        cluster_scan<3>(ctl, 1, crank, sums, Pz, Xz, tot);
+        const float Zp = tot[0], Ssum = tot[1], Zq = tot[2];
+        if (p.greedy) amax = cluster_min_int(ctl, 3, crank, amax);
+
+        // ------------------------------------------------------------ pass 3: residual + inverse CDF
+        const int x = (i < p.k) ? p.draft_tokens[b * p.k + i] : -1;
+        const bool x_ok = (i < p.k) && x >= 0 && x < V;
+        const uint32_t scal0 = mapa(smem_u32(&ctl->scal[0]), 0);
+        if (x_ok) {
+            const int jx = x >> 2, sx = jx / kSlabVec, lx = jx - sx * kSlabVec;
+            if (lx / kThreads == (int)crank && lx % kThreads == tid) {
+                float epx = 0.f, eqx = 0.f;
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (s == sx) {
+                        const float pe[4] = {zt[s].x, zt[s].y, zt[s].z, zt[s].w};
+                        const float qe[4] = {zq[s].x, zq[s].y, zq[s].z, zq[s].w};
+                        epx = pe[x & 3];
+                        eqx = qe[x & 3];
+                    }
+                st_cluster_f32(scal0 + 0, epx);
+                if (has_draft) st_cluster_f32(scal0 + 4, eqx);
+            }
+        }
+        if (!p.greedy) {
+            // residual weights replace the draft registers: r = max(0, fma(e_p, Z_q, -(e_q * Z_p)))
+            float rs[1] = {0.0f};
+            const float2 zqv = make_float2(Zq, Zq), nzpv = make_float2(-Zp, -Zp);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                if (have[s]) {
+                    float4 r4;
+                    if (has_draft) {
+                        const float2 w0 = __fmul2_rn(make_float2(zq[s].x, zq[s].y), nzpv);   // -(e_q * Z_p), exact sign flip
+                        const float2 w1 = __fmul2_rn(make_float2(zq[s].z, zq[s].w), nzpv);
+                        const float2 r0 = __ffma2_rn(make_float2(zt[s].x, zt[s].y), zqv, w0);
+                        const float2 r1 = __ffma2_rn(make_float2(zt[s].z, zt[s].w), zqv, w1);
+                        r4 = make_float4(fmaxf(r0.x, 0.0f), fmaxf(r0.y, 0.0f), fmaxf(r1.x, 0.0f), fmaxf(r1.y, 0.0f));
+                    } else {
+                        r4 = zt[s];
+                    }
+                    rs[0] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(rs[0], r4.x), r4.y), r4.z), r4.w);
+                    zq[s] = r4;
+                }
+            }
+            float Pr[1], Xr[1], Rt[1];
+            cluster_scan<1>(ctl, 2, crank, rs, Pr, Xr, Rt);
+            float ur = (float)p.u_resid[b];
+            if (!(ur >= 0.0f)) ur = 0.0f;
+            if (ur >= 1.0f) ur = 0x1.fffffep-1f;
+            const float tau = __fmul_rn(ur, Rt[0]);
+            if (Rt[0] > 0.0f && Pr[0] > tau && Xr[0] <= tau) {   // exactly one thread of the cluster
+                float c = Xr[0], epy = 0.0f, ep_last = 0.0f;
+                int sel = -1, last_pos = -1;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    if (have[s] && sel < 0) {
+                        const int j = s * kSlabVec + (int)crank * kThreads + tid;
+                        const float rr[4] = {zq[s].x, zq[s].y, zq[s].z, zq[s].w};
+                        const float pe[4] = {zt[s].x, zt[s].y, zt[s].z, zt[s].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (sel < 0) {
+                                if (rr[e] > 0.0f) {
+                                    last_pos = j * 4 + e;
+                                    ep_last = pe[e];
+                                }
+                                c = __fadd_rn(c, rr[e]);
+                                if (c > tau) {
+                                    sel = j * 4 + e;
+                                    epy = pe[e];
+                                }
+                            }
+                        }
+                    }
+                }
+                const int y = sel >= 0 ? sel : last_pos;
+                st_cluster_f32(scal0 + 8, sel >= 0 ? epy : ep_last);
+                st_cluster_u32(scal0 + 12, (uint32_t)y);
+                st_cluster_f32(scal0 + 16, 1.0f);
+            }
+        }
+        cluster_sync();
+        if (crank == 0 && tid == 0)
+            row_epilogue(p, ctl, row, b, i, x, x_ok, has_draft, amax, m1, m2, Zp, Zq, Ssum, zt_g);
+    }
+    cluster_sync();
+}
+
+static int g_max_clusters[2 * kMaxSlabs + 16];
+int g_sampler_impl = 1;   // 1: register-resident kernel when V allows, 0: always the shared-memory kernel
 
 size_t reject_sample_workspace_bytes(int B, int k) {
     const size_t rows = (size_t)B * (k + 1);
@@ -492,7 +770,26 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
     p.row_lpx = reinterpret_cast<float*>(p.row_cand + rows);
     p.row_lpy = p.row_lpx + rows;
 
-    const size_t smem = (size_t)num_slabs * kSlabBytesPerCta * 2 + sizeof(SmemCtl);
+    // register-resident kernel for NS in {1, 2, 4, 7, 10}; the shared-memory-resident kernel above covers larger V
+    static const int kRegNs[] = {1, 2, 4, 7, 10};
+    int ns = 0;
+    if (g_sampler_impl != 0)
+        for (int c : kRegNs)
+            if (c >= num_slabs) {
+                ns = c;
+                break;
+            }
+    const void* fn = (const void*)reject_sample_kernel;
+    switch (ns) {
+        case 1: fn = (const void*)reject_sample_reg_kernel<1>; break;
+        case 2: fn = (const void*)reject_sample_reg_kernel<2>; break;
+        case 4: fn = (const void*)reject_sample_reg_kernel<4>; break;
+        case 7: fn = (const void*)reject_sample_reg_kernel<7>; break;
+        case 10: fn = (const void*)reject_sample_reg_kernel<10>; break;
+        default: break;
+    }
+    const int smem_slabs = ns ? ns : num_slabs;
+    const size_t smem = (size_t)smem_slabs * kSlabBytesPerCta * 2 + sizeof(SmemCtl);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -504,23 +801,22 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (!g_attr_set) {
+    const int slot = ns ? kMaxSlabs + 1 + ns : num_slabs;   // cache index of (kernel, footprint)
+    if (g_max_clusters[slot] == 0) {
         int dev = 0, optin = 0;
         ASD_CUDA(cudaGetDevice(&dev));
         ASD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        ASD_CUDA(cudaFuncSetAttribute(reject_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-        g_attr_set = 1;
-    }
-    if (g_max_clusters[num_slabs] == 0) {
+        ASD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         cfg.gridDim = dim3(kCluster * 148);
         int n = 0;
-        ASD_CUDA(cudaOccupancyMaxActiveClusters(&n, reject_sample_kernel, &cfg));
+        ASD_CUDA(cudaOccupancyMaxActiveClusters(&n, fn, &cfg));
         if (n <= 0) return set_error("asd_reject_sample: no cluster of 8 CTAs fits on this device");
-        g_max_clusters[num_slabs] = n;
+        g_max_clusters[slot] = n;
     }
-    const int nclusters = (int)(rows < (size_t)g_max_clusters[num_slabs] ? rows : g_max_clusters[num_slabs]);
+    const int nclusters = (int)(rows < (size_t)g_max_clusters[slot] ? rows : g_max_clusters[slot]);
     cfg.gridDim = dim3(kCluster * nclusters);
-    ASD_CUDA(cudaLaunchKernelEx(&cfg, reject_sample_kernel, p));
+    void* args[] = {(void*)&p};
+    ASD_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
     count_launch(1);
     return 0;
 }

@@ -55,6 +55,9 @@ ASD_API void asd_reset_launch_count(void);
  * token per row from softmax(target/T) (used for the draft model's own sampling).
  */
 ASD_API size_t asd_reject_sample_workspace_bytes(int B, int k);
+/* 1 (default): register-resident kernel with TMA prefetch of the next row when V <= 163840;
+ * 0: always the shared-memory-resident kernel (same arithmetic contract, bit-identical results) */
+ASD_API void asd_reject_sample_set_impl(int impl);
 ASD_API int asd_reject_sample(const float* target_logits, const float* draft_logits, const int32_t* draft_tokens,
                       const double* u_accept, const double* u_resid, int B, int k, int V, float temperature,
                       uint8_t* accept_mask, int32_t* accepted_len, int32_t* out_tokens, float* out_logprobs,

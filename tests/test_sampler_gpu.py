@@ -50,6 +50,20 @@ def test_parity_sampling(B, k, V, T):
     compare(run_gpu(tl, dl, dt, ua, ur, T), oracle.reject_sample(tl, dl, dt, ua, ur, T))
 
 
+@pytest.mark.parametrize("B,k,V,T", [(3, 4, 152064, 0.7), (2, 3, 16388, 0.3), (1, 8, 151936, 1.0)])
+def test_both_kernels_agree_bit_for_bit(B, k, V, T):
+    """the shared-memory-resident and the register-resident kernels implement one contract"""
+    from asd_b200 import lib
+    tl, dl, dt, ua, ur = make_case(B, k, V, seed=77, T=T)
+    ref = oracle.reject_sample(tl, dl, dt, ua, ur, T)
+    try:
+        lib().asd_reject_sample_set_impl(0)
+        compare(run_gpu(tl, dl, dt, ua, ur, T), ref)
+    finally:
+        lib().asd_reject_sample_set_impl(1)
+    compare(run_gpu(tl, dl, dt, ua, ur, T), ref)
+
+
 def test_parity_all_accept_all_reject_and_bad_tokens():
     B, k, V, T = 4, 5, 152064, 0.7
     tl, _, dt, ua, ur = make_case(B, k, V, seed=1, T=T)
