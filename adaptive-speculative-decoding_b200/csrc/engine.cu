@@ -182,6 +182,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             prod.sumsq_out = e->sumsq;
             prod.ld = Mx;
             prod.resid_bf = e->resid_bf;
+            prod.ln_w = next_ln;
         }
         {
             PROF(PROF_GEMM);

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
                     const float v = a.accumulate ? *o + acc : acc;
                     *o = v;
                     if (emit) {
-                        a.norm.resid_bf[(size_t)m * a.ldo + n] = __float2bfloat16(v);
+                        a.norm.resid_bf[(size_t)m * a.ldo + n] = __float2bfloat16(v * __bfloat162float(a.norm.ln_w[n]));
                         sq = v * v;
                     }
                 }
@@ -536,7 +536,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     if (a.norm.sumsq_out != nullptr) {
         if (!pl.reduce || pl.ksplit < 4 || pl.mode != GEMM_OUT_F32)
             return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction with ksplit >= 4");
-        if (!a.norm.resid_bf) return set_error("gemm: fused norm producer needs resid_bf");
+        if (!a.norm.resid_bf || !a.norm.ln_w) return set_error("gemm: fused norm producer needs resid_bf and ln_w");
     }
     a.qkv = QkvEpilogue{};
     if (pl.mode == GEMM_OUT_QKV) {

@@ -8,15 +8,18 @@ namespace asd {
 
 enum GemmOut { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_SWIGLU = 2, GEMM_OUT_QKV = 3 };
 
-// Fused RMSNorm.  Consumer side: x is the UN-normalised bf16 residual, the ln weight is folded into W, and the
-// epilogue scales token m by rstd[m] = rsqrt(sum_t sumsq[t][m] / hidden + eps).  Producer side (fp32
-// accumulate epilogue): besides the fp32 residual it writes the bf16 copy and this tile's sum of squares.
+// Fused RMSNorm.  Producer side (fp32 accumulate epilogue of the O / down projection): besides the fp32
+// residual v it writes x = bf16(v * ln_w[n]) (the next norm's weight applied per column, NOT yet divided by
+// the rms) and this tile's sum of v^2 per token.  Consumer side: the GEMM reads x and its epilogue scales
+// token m by rstd[m] = rsqrt(sum_t sumsq[t][m] / hidden + eps) - algebraically RMSNorm(v) * ln_w @ W^T with the
+// same bf16 rounding points as the unfused kernels.
 struct NormFusion {
     const float* sumsq_in = nullptr;   // consumer: [parts][ld]
     int parts = 0, ld = 0, hidden = 0;
     float eps = 0.f;
     float* sumsq_out = nullptr;        // producer: [n_tiles][ld]
-    __nv_bfloat16* resid_bf = nullptr; // producer: [M][ldo] bf16 copy of the updated residual
+    __nv_bfloat16* resid_bf = nullptr; // producer: [M][ldo] bf16(v * ln_w)
+    const __nv_bfloat16* ln_w = nullptr; // producer: [N] weight of the NEXT RMSNorm
 };
 
 // extra operands of the fused QKV epilogue (bias + rotate-half RoPE + q store + paged K/V append)

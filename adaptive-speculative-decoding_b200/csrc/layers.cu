@@ -80,9 +80,11 @@ __global__ void __launch_bounds__(kNormThreads) add_norm_kernel(float* __restric
         for (int i = 0; i < kNormMaxVec; ++i) {
             const int c = threadIdx.x + i * kNormThreads;
             if (c < nvec) {
+                const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(w) + 2 * c;
+                const float2 w0 = __bfloat1622float2(wp[0]), w1 = __bfloat1622float2(wp[1]);
                 __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(resid_bf + (size_t)m * h) + 2 * c;
-                op[0] = __floats2bfloat162_rn(v[i].x, v[i].y);
-                op[1] = __floats2bfloat162_rn(v[i].z, v[i].w);
+                op[0] = __floats2bfloat162_rn(v[i].x * w0.x, v[i].y * w0.y);
+                op[1] = __floats2bfloat162_rn(v[i].z * w1.x, v[i].w * w1.y);
             }
         }
         if (threadIdx.x == 0) sumsq0[m] = tot;

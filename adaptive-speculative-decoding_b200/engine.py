@@ -53,7 +53,7 @@ class QwenEngine:
         self.inv_freq = inv.to(self.device)
         self._weights = []   # keep tensors alive
         self._index_cache = {}
-        self.fuse_norm = bool(fuse_norm)   # RMSNorm folded into the consumer GEMMs (weights folded at load)
+        self.fuse_norm = bool(fuse_norm)   # RMSNorm fused into the GEMM epilogues (no separate norm kernels)
         self.set_option("fuse_norm", int(self.fuse_norm))
         self._globals_set = False
 
@@ -83,14 +83,10 @@ class QwenEngine:
     def load_hf_weights(self, w: Dict[str, torch.Tensor]):
         """HF-named Qwen2 state dict (any device) -> packed bf16 engine layout on this rank."""
         for l in range(self.cfg.num_hidden_layers):
-            self._set_layer(l, pack_layer(w, self.cfg, l, self.tp_rank, self.tp_size, self.device, self.fuse_norm))
+            self._set_layer(l, pack_layer(w, self.cfg, l, self.tp_rank, self.tp_size, self.device))
         dev = lambda t: t.to(device=self.device, dtype=torch.bfloat16).contiguous()
         embed = dev(w["model.embed_tokens.weight"])
-        head_src = w.get("lm_head.weight", w["model.embed_tokens.weight"])
-        if self.fuse_norm:   # final RMSNorm weight folded into the lm_head columns (a separate copy when tied)
-            head = dev(head_src.float() * w["model.norm.weight"].float()[None, :].to(head_src.device))
-        else:
-            head = embed if "lm_head.weight" not in w else dev(head_src)
+        head = embed if "lm_head.weight" not in w else dev(w["lm_head.weight"])
         self._set_globals(embed, dev(w["model.norm.weight"]), head)
         return self
 

@@ -143,8 +143,8 @@ ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_all
 /* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
  * "reduce" (1 in-cluster split-K reduction with fused residual add, 0 fp32 slices summed by the glue
  * kernels), "fuse_rope" (1: bias + RoPE + q store + paged K/V append in the QKV GEMM epilogue),
- * "fuse_norm" (1: RMSNorm folded into the consumer GEMMs; the caller must have multiplied the ln weights into
- * wqkv / wgateup / lm_head columns beforehand - asd_b200.models.qwen2.pack_layer(fold_norm=True)),
+ * "fuse_norm" (1: RMSNorm fused into the GEMMs: the O / down epilogues emit bf16(resid * ln_w) and the
+ * per-token sum of squares, the consuming QKV / gate|up / lm_head epilogues apply rstd),
  * "attn_target_ctas", "glue_pdl", "ksplit", "stages" (0 = automatic), "profile" (0/1) */
 ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
 /* With option "profile" = 1 every launch is bracketed by CUDA events on the launching stream;
