@@ -60,6 +60,9 @@ def lib() -> ctypes.CDLL:
         "asd_engine_set_kv": (i32, [vp, vp, i32, vp, i32, i32]),
         "asd_engine_set_allreduce": (i32, [vp, vp, vp]),
         "asd_engine_set_option": (i32, [vp, c.c_char_p, i32]),
+        "asd_engine_ipc_export": (i32, [vp, vp]),
+        "asd_engine_ipc_import": (i32, [vp, vp]),
+        "asd_engine_tp_error": (i32, [vp]),
         "asd_engine_profile_read": (i32, [vp, vp, vp, i32]),
         "asd_engine_forward": (i32, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, c.c_longlong, vp]),
     }

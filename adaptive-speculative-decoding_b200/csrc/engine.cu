@@ -62,6 +62,14 @@ struct Engine {
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
+    // fused peer-memory all-reduce (CUDA IPC): double-buffered partials + flag array, local and peer views
+    float* tp_buf[2] = {nullptr, nullptr};
+    uint32_t* tp_flags = nullptr;
+    int* tp_error = nullptr;
+    const float* peer_buf[2][8] = {};
+    uint32_t* peer_flags[8] = {};
+    bool p2p = false;
+    uint32_t tp_epoch = 0;
     // profiling (option "profile"): CUDA-event pairs around every launch, by kernel class
     int profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -140,7 +148,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     if (ensure_plans(e, M, &P)) return -1;
     const int h = c.hidden, nh = c.n_heads, nkv = c.n_kv_heads, hd = c.head_dim, Mx = c.max_tokens;
     const bool tp = c.tp_size > 1;
-    if (tp && !e->allreduce) return set_error("engine: tp_size > 1 but no all-reduce installed");
+    if (tp && !e->allreduce && !e->p2p) return set_error("engine: tp_size > 1 but no all-reduce installed");
 
     // attention split selection: fill the SMs once, >= 4 key tiles per split, bounded workspace
     int nsplit = (e->attn_target_ctas + nseq * nkv / 2) / (nseq * nkv);
@@ -177,6 +185,8 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
                                 const __nv_bfloat16* next_ln) -> int {
         const bool fuse = !tp && (pl.reduce || pl.ksplit == 1);
         const bool emit = fn && fuse && pl.reduce && pl.ksplit >= 4;
+        const bool p2p_ok = tp && e->p2p && (pl.reduce || pl.ksplit == 1);
+        if (p2p_ok) ++e->tp_epoch;
         NormFusion prod;
         if (emit) {
             prod.sumsq_out = e->sumsq;
@@ -186,8 +196,8 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         }
         {
             PROF(PROF_GEMM);
-            if (gemm_launch(pl, tw, tx, fuse ? (void*)e->resid : (void*)e->part, h, h, e->pdl, s, fuse, nullptr,
-                            emit ? &prod : nullptr))
+            void* dst = fuse ? (void*)e->resid : (p2p_ok ? (void*)e->tp_buf[e->tp_epoch & 1] : (void*)e->part);
+            if (gemm_launch(pl, tw, tx, dst, h, h, e->pdl, s, fuse, nullptr, emit ? &prod : nullptr))
                 return -1;
         }
         if (emit) {
@@ -195,6 +205,15 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             return 0;
         }
         int ns = fuse ? 0 : (pl.reduce ? 1 : pl.ksplit);
+        if (tp && p2p_ok) {
+            // one kernel: all-reduce over NVLink peer memory + residual add + norm statistics
+            PROF(PROF_COMM);
+            parts = 1;
+            const uint32_t ep = e->tp_epoch;   // the GEMM above wrote tp_buf[ep & 1]
+            return launch_tp_allreduce_norm(e->peer_buf[ep & 1], e->peer_flags, c.tp_rank, c.tp_size, ep, e->tp_error,
+                                            e->resid, next_ln, fn ? nullptr : (next_ln ? e->xnorm : nullptr), M, h,
+                                            c.rms_eps, fn ? e->resid_bf : nullptr, fn ? e->sumsq : nullptr, s);
+        }
         if (tp) {
             PROF(PROF_COMM);
             if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
@@ -352,6 +371,16 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
     alloc((void**)&e->sumsq_sel, Mx * (size_t)((c.hidden + 127) / 128) * 4);
     alloc((void**)&e->tickets, Mx * c.n_kv_heads * 4);
     if (ok && cudaMemset(e->tickets, 0, Mx * c.n_kv_heads * 4) != cudaSuccess) ok = false;
+    if (c.tp_size > 1) {
+        alloc((void**)&e->tp_buf[0], Mx * c.hidden * 4);
+        alloc((void**)&e->tp_buf[1], Mx * c.hidden * 4);
+        alloc((void**)&e->tp_flags, 256);
+        alloc((void**)&e->tp_error, 256);
+        if (ok) {
+            cudaMemset(e->tp_flags, 0, 256);
+            cudaMemset(e->tp_error, 0, 256);
+        }
+    }
     alloc((void**)&e->xnorm, Mx * c.hidden * 2);
     alloc((void**)&e->xsel, Mx * c.hidden * 2);
     alloc((void**)&e->q, Mx * e->qdim * 2);
@@ -368,7 +397,7 @@ void asd_engine_destroy(asd_engine_t* h) {
     Engine* e = reinterpret_cast<Engine*>(h);
     if (!e) return;
     void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->tickets, e->rope_cs, e->resid_bf, e->sumsq,
-                    e->sumsq_sel, e->xnorm, e->xsel, e->q, e->attn, e->act};
+                    e->sumsq_sel, e->tp_buf[0], e->tp_buf[1], e->tp_flags, e->tp_error, e->xnorm, e->xsel, e->q, e->attn, e->act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete e;
@@ -431,6 +460,49 @@ int asd_engine_set_allreduce(asd_engine_t* h, void* comm, void* nccl_allreduce_f
     return 0;
 }
 
+int asd_engine_ipc_export(asd_engine_t* h, void* handles_out) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !handles_out || !e->tp_buf[0]) return set_error("asd_engine_ipc_export: engine has no TP buffers");
+    cudaIpcMemHandle_t* out = static_cast<cudaIpcMemHandle_t*>(handles_out);
+    ASD_CUDA(cudaIpcGetMemHandle(&out[0], e->tp_buf[0]));
+    ASD_CUDA(cudaIpcGetMemHandle(&out[1], e->tp_buf[1]));
+    ASD_CUDA(cudaIpcGetMemHandle(&out[2], e->tp_flags));
+    return 0;
+}
+
+int asd_engine_ipc_import(asd_engine_t* h, const void* all_handles) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !all_handles || !e->tp_buf[0]) return set_error("asd_engine_ipc_import: engine has no TP buffers");
+    const int world = e->c.tp_size, rank = e->c.tp_rank;
+    if (world > 8) return set_error("asd_engine_ipc_import: tp_size <= 8");
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            e->peer_buf[0][r] = e->tp_buf[0];
+            e->peer_buf[1][r] = e->tp_buf[1];
+            e->peer_flags[r] = e->tp_flags;
+            continue;
+        }
+        void *b0 = nullptr, *b1 = nullptr, *fl = nullptr;
+        ASD_CUDA(cudaIpcOpenMemHandle(&b0, hs[r * 3 + 0], cudaIpcMemLazyEnablePeerAccess));
+        ASD_CUDA(cudaIpcOpenMemHandle(&b1, hs[r * 3 + 1], cudaIpcMemLazyEnablePeerAccess));
+        ASD_CUDA(cudaIpcOpenMemHandle(&fl, hs[r * 3 + 2], cudaIpcMemLazyEnablePeerAccess));
+        e->peer_buf[0][r] = static_cast<const float*>(b0);
+        e->peer_buf[1][r] = static_cast<const float*>(b1);
+        e->peer_flags[r] = static_cast<uint32_t*>(fl);
+    }
+    e->p2p = true;
+    return 0;
+}
+
+int asd_engine_tp_error(asd_engine_t* h) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e || !e->tp_error) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, e->tp_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
+
 int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     Engine* e = reinterpret_cast<Engine*>(h);
     if (!e || !name) return set_error("asd_engine_set_option: NULL argument");
@@ -443,6 +515,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
     else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
+    else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;
     else if (!strcmp(name, "profile")) {
         e->profile = value;
         e->ev_used.clear();

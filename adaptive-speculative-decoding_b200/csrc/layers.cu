@@ -126,6 +126,124 @@ int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_s
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-parallel boundary, fused: one-shot all-reduce over NVLink peer memory + residual add + RMSNorm
+// statistics in ONE kernel (replaces ncclAllReduce + add_norm).  Every rank's row-parallel GEMM leaves its
+// fp32 partial [M, h] in a buffer that all peers have mapped (CUDA IPC); this kernel
+//   1. publishes "my partial for epoch e is ready" into every peer's flag array (system-scope release),
+//   2. waits until every peer's flag for this epoch has arrived (acquire, bounded spin),
+//   3. loads the `world` partials straight from peer memory (NVLink P2P loads, L1 bypassed), adds them in rank
+//      order - so all ranks compute bit-identical sums - plus the residual, and emits the fp32 residual, the
+//      bf16 operand of the next GEMM and the per-token sum of squares exactly like add_norm_kernel.
+// The partial buffers are double-buffered by the caller; a rank can only reach all-reduce n+1's flag after it
+// finished reading all-reduce n, so when a GEMM overwrites buffer n%2 again (for all-reduce n+2) every peer is
+// done with it.
+struct TpPeers {
+    const float* buf[8];   // this epoch's partial buffer of every rank (peer-mapped pointers)
+    uint32_t* flags[8];    // flag array of every rank: flags[p][r] = last epoch rank r published to rank p
+    int rank, world;
+    uint32_t epoch;
+    int* error;            // set to 1 if a peer never showed up
+};
+
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kNormThreads) tp_allreduce_norm_kernel(
+    const TpPeers tp, float* __restrict__ resid, const __nv_bfloat16* __restrict__ w,
+    __nv_bfloat16* __restrict__ xnorm, int h, float eps, __nv_bfloat16* __restrict__ resid_bf,
+    float* __restrict__ sumsq0) {
+    __shared__ float scratch[kNormThreads / 32];
+    grid_dep_launch();
+    if (blockIdx.x == 0 && threadIdx.x < tp.world && (int)threadIdx.x != tp.rank) {
+        __threadfence_system();   // the GEMM that produced my partial finished before this kernel started
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tp.flags[threadIdx.x] + tp.rank), "r"(tp.epoch)
+                     : "memory");
+    }
+    if (threadIdx.x < tp.world && (int)threadIdx.x != tp.rank) {
+        const uint32_t* f = tp.flags[tp.rank] + threadIdx.x;
+        uint32_t seen;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+            if ((int)(seen - tp.epoch) >= 0) break;
+            if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; fail loudly instead of hanging the GPU
+                *tp.error = 1;
+                break;
+            }
+        } while (true);
+    }
+    __syncthreads();
+    const int m = blockIdx.x, nvec = h >> 2;
+    float4 v[kNormMaxVec];
+    float ss = 0.0f;
+    float4* rrow = reinterpret_cast<float4*>(resid + (size_t)m * h);
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+        const int c = threadIdx.x + i * kNormThreads;
+        if (c < nvec) {
+            float4 x = rrow[c];
+            for (int r = 0; r < tp.world; ++r) {
+                const float4 p = ld_peer_f4(tp.buf[r] + (size_t)m * h + 4 * c);
+                x.x += p.x;
+                x.y += p.y;
+                x.z += p.z;
+                x.w += p.w;
+            }
+            rrow[c] = x;
+            v[i] = x;
+            ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+    }
+    const float tot = block_sum(ss, scratch);
+    const float inv = rsqrtf(tot / (float)h + eps);
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+        const int c = threadIdx.x + i * kNormThreads;
+        if (c < nvec && w != nullptr) {
+            const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(w) + 2 * c;
+            const float2 w0 = __bfloat1622float2(wp[0]), w1 = __bfloat1622float2(wp[1]);
+            if (resid_bf != nullptr) {
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(resid_bf + (size_t)m * h) + 2 * c;
+                op[0] = __floats2bfloat162_rn(v[i].x * w0.x, v[i].y * w0.y);
+                op[1] = __floats2bfloat162_rn(v[i].z * w1.x, v[i].w * w1.y);
+            }
+            if (xnorm != nullptr) {
+                __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(xnorm + (size_t)m * h) + 2 * c;
+                op[0] = __floats2bfloat162_rn(v[i].x * inv * w0.x, v[i].y * inv * w0.y);
+                op[1] = __floats2bfloat162_rn(v[i].z * inv * w1.x, v[i].w * inv * w1.y);
+            }
+        }
+    }
+    if (sumsq0 != nullptr && threadIdx.x == 0) sumsq0[m] = tot;
+}
+
+int launch_tp_allreduce_norm(const float* const* peer_bufs, uint32_t* const* peer_flags, int rank, int world,
+                             uint32_t epoch, int* error, float* resid, const __nv_bfloat16* w, __nv_bfloat16* xnorm,
+                             int M, int h, float eps, __nv_bfloat16* resid_bf, float* sumsq0, cudaStream_t stream) {
+    if (world > 8) return set_error("tp all-reduce: world size <= 8");
+    if (h % 4 || h > kNormThreads * kNormMaxVec * 4) return set_error("tp all-reduce: hidden must be %%4 and <= 8192");
+    TpPeers tp;
+    for (int r = 0; r < 8; ++r) {
+        tp.buf[r] = r < world ? peer_bufs[r] : nullptr;
+        tp.flags[r] = r < world ? peer_flags[r] : nullptr;
+    }
+    tp.rank = rank;
+    tp.world = world;
+    tp.epoch = epoch;
+    tp.error = error;
+    tp_allreduce_norm_kernel<<<M, kNormThreads, 0, stream>>>(tp, resid, w, xnorm, h, eps, resid_bf, sumsq0);
+    ASD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
 // reduce K-split slices into slice 0 (used before a tensor-parallel all-reduce)
 __global__ void reduce_slices_kernel(float* __restrict__ part, int nslices, size_t slice_stride, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -114,6 +114,23 @@ class QwenEngine:
         check(lib().asd_engine_profile_read(self.h, ms, n, 5), "asd_engine_profile_read")
         return {c: (ms[i], n[i]) for i, c in enumerate(self.PROFILE_CLASSES)}
 
+    def enable_p2p(self, group=None):
+        """Exchange CUDA-IPC handles of the TP partial buffers with the other ranks (torch.distributed) and
+        switch the row-parallel boundaries to the fused peer-memory all-reduce kernel."""
+        import torch.distributed as dist
+        mine = ctypes.create_string_buffer(3 * 64)
+        check(lib().asd_engine_ipc_export(self.h, mine), "asd_engine_ipc_export")
+        table = [None] * self.tp_size
+        dist.all_gather_object(table, bytes(mine.raw), group=group)
+        blob = ctypes.create_string_buffer(b"".join(table), 3 * 64 * self.tp_size)
+        with torch.cuda.device(self.device):
+            check(lib().asd_engine_ipc_import(self.h, blob), "asd_engine_ipc_import")
+        dist.barrier(group=group)
+        return self
+
+    def tp_error(self) -> int:
+        return int(lib().asd_engine_tp_error(self.h))
+
     def set_allreduce(self, comm_ptr: int, fn_ptr: int):
         check(lib().asd_engine_set_allreduce(self.h, ctypes.c_void_p(comm_ptr), ctypes.c_void_p(fn_ptr)),
               "asd_engine_set_allreduce")

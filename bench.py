@@ -78,7 +78,7 @@ def config_dict(wl, n_gpus, extra=None):
     c = {"workload": f"{wl['draft'].name} draft -> {wl['target'].name} target, bf16, chain k={wl['k']}, batch {wl['B']}, "
                      f"prefix {wl['prefix']}, temperature {wl['T']}, random-init weights, synthetic prompts",
          "batch": wl["B"], "k": wl["k"], "prefix": wl["prefix"], "temperature": wl["T"],
-         "parallelism": "single-gpu" if n_gpus == 1 else f"target tp{n_gpus}, draft replicated",
+         "parallelism": "single-gpu" if n_gpus == 1 else f"target tp{n_gpus} (fused NVLink all-reduce), draft replicated",
          "l2": "inputs larger than L2 (64 GB of weights streamed per verify step; no flush needed)"}
     if extra:
         c.update(extra)
@@ -138,7 +138,9 @@ def run_ours(args):
     comm = None
     if world > 1:
         comm = NcclComm(rank, world)
-        target.set_allreduce(comm.comm_ptr, comm.allreduce_fn_ptr)
+        target.set_allreduce(comm.comm_ptr, comm.allreduce_fn_ptr)     # NCCL path (fallback / --opt p2p=0)
+        if not args.nccl_only:
+            target.enable_p2p()                                        # fused peer-memory all-reduce kernel
     for opt in args.opt or []:
         name, val = opt.split("=")
         target.set_option(name, int(val))
@@ -281,6 +283,7 @@ def main():
     ap.add_argument("--temperature", type=float, default=0.7)
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="TP boundaries through ncclAllReduce instead of the fused kernel")
     ap.add_argument("--opt", action="append", help="engine option name=value (e.g. pdl=0, attn_impl=0)")
     args = ap.parse_args()
     if args.warmup < 3:

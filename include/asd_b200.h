@@ -140,6 +140,14 @@ ASD_API int asd_engine_set_kv(asd_engine_t* e, void* kv_pool, int num_pages, con
 /* comm: ncclComm_t; nccl_allreduce_fn: address of ncclAllReduce from the NCCL the process loaded.
  * Called (fp32 sum, in place) after the O and down projections when tp_size > 1. */
 ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_allreduce_fn);
+/* Fused tensor-parallel boundary over NVLink peer memory (preferred to the NCCL path above): every rank
+ * exports CUDA-IPC handles of its two partial buffers and its flag array (3 x 64 bytes), the host
+ * all-gathers them (rank-major, world x 3 x 64 bytes) and each rank imports the table.  From then on the O /
+ * down projections are followed by ONE kernel that all-reduces through P2P loads, adds the residual and emits
+ * the norm statistics.  asd_engine_tp_error returns 1 if a peer ever failed to show up within the spin bound. */
+ASD_API int asd_engine_ipc_export(asd_engine_t* e, void* handles_out);
+ASD_API int asd_engine_ipc_import(asd_engine_t* e, const void* all_handles);
+ASD_API int asd_engine_tp_error(asd_engine_t* e);
 /* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
  * "reduce" (1 in-cluster split-K reduction with fused residual add, 0 fp32 slices summed by the glue
  * kernels), "fuse_rope" (1: bias + RoPE + q store + paged K/V append in the QKV GEMM epilogue),

@@ -1,0 +1,66 @@
+"""Tensor-parallel engine on 2 GPUs (skipped on a single-GPU box): both TP boundaries - the fused
+peer-memory all-reduce kernel and the NCCL path - must reproduce the oracle's logits, and all ranks must
+produce bit-identical logits (they stay in lock step without exchanging tokens)."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, p2p, out):
+    import torch.distributed as dist
+    from asd_b200.engine import QwenEngine
+    from asd_b200.models.qwen2 import Qwen2Config, random_hf_weights
+    from asd_b200.parallel import NcclComm
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = Qwen2Config(512, 2, 8, 2, 1024, 4096, head_dim=128, name="tp-test")
+    w = random_hf_weights(cfg, seed=11)
+    ids = torch.randint(0, cfg.vocab_size, (3, 70), generator=torch.Generator().manual_seed(5))
+    dev = torch.device("cuda", rank)
+    eng = QwenEngine(cfg, max_seqs=3, max_seq_len=96, max_tokens=64, tp_rank=rank, tp_size=world, device=dev)
+    eng.load_hf_weights(w)
+    comm = NcclComm(rank, world)
+    eng.set_allreduce(comm.comm_ptr, comm.allreduce_fn_ptr)
+    if p2p:
+        eng.enable_p2p()
+    slots = torch.arange(3, dtype=torch.int32, device=dev)
+    idc = ids.to(dev).to(torch.int32)
+    eng.prefill(idc[:, :64], slots)
+    ver = eng.forward_uniform(idc[:, 64:].contiguous(), torch.full((3,), 64, dtype=torch.int32, device=dev), slots, 70)
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(ver) for _ in range(world)]
+    dist.all_gather(gathered, ver)
+    if rank == 0:
+        from oracle.model_oracle import qwen2_forward
+        ref = qwen2_forward(w, cfg, ids)[:, 64:]
+        got = ver.view(3, 6, -1).cpu()
+        out["err"] = float((got - ref).abs().max())
+        out["agree"] = float((got.argmax(-1) == ref.argmax(-1)).float().mean())
+        out["identical"] = bool(all(torch.equal(gathered[0], g) for g in gathered))
+        out["tp_error"] = eng.tp_error()
+    dist.barrier()
+    comm.destroy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("p2p", [True, False])
+def test_tp2_logits_match_oracle(p2p):
+    import torch.multiprocessing as mp
+    out = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), p2p, out), nprocs=2, join=True)
+    assert out["err"] <= 2e-2 and out["agree"] >= 0.99, dict(out)
+    assert out["identical"] and out["tp_error"] == 0, dict(out)
