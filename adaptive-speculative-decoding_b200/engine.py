@@ -141,6 +141,8 @@ class QwenEngine:
                 want_logits: bool = True, logits_ld: int = 0):
         """int32 CUDA tensors; returns fp32 logits [rows, vocab] (or None)."""
         M, nseq = tokens.numel(), seq_slot.numel()
+        for t in (tokens, positions, token_slot, cu_q, seq_slot):
+            assert t.dtype == torch.int32 and t.is_contiguous() and t.is_cuda, "int32 contiguous CUDA tensors"
         n_rows = 0 if not want_logits else (M if logit_rows is None else logit_rows.numel())
         if n_rows and logits_out is None:
             logits_out = torch.empty(n_rows, self.cfg.vocab_size, dtype=torch.float32, device=self.device)
@@ -173,7 +175,8 @@ class QwenEngine:
         positions = (start_pos[:, None] + ix["ar"]).reshape(-1)
         token_slot = slots[:, None].expand(nseq, q).reshape(-1) if q > 1 else slots
         rows = ix["last_rows"] if (last_only and want_logits and q > 1) else None
-        return self.forward(tokens2d.reshape(-1), positions, token_slot.contiguous(), ix["cu_q"], slots, q,
+        return self.forward(tokens2d.reshape(-1).contiguous(), positions.contiguous(), token_slot.contiguous(),
+                            ix["cu_q"], slots.contiguous(), q,
                             max_kv_len, rows, logits_out, want_logits, logits_ld)
 
     def prefill(self, prompt_ids: torch.Tensor, slots: torch.Tensor, chunk: int = 0, want_logits: bool = True):

@@ -85,6 +85,17 @@ def test_engine_unfused_paths(opts):
     eng.close()
 
 
+def test_prefill_with_single_token_tail_chunk():
+    """chunk sizes that leave a 1-token tail (a strided [B, 1] view of the prompt) must still be correct"""
+    cfg = Qwen2Config(512, 2, 8, 2, 1024, 4096, head_dim=128, name="tail")
+    w = random_hf_weights(cfg, seed=11)
+    ids = torch.randint(0, cfg.vocab_size, (3, 70), generator=torch.Generator().manual_seed(5))
+    ref = qwen2_forward(w, cfg, ids)
+    ver, last = run_engine(cfg, w, ids, 6, 1, chunk=21)
+    check(ver, ref[:, 64:])
+    check(last, ref[:, 63])
+
+
 def test_engine_hf_golden_weights():
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "qwen2_tiny_golden.npz"))
     w = {k[3:]: torch.from_numpy(z[k]).view(torch.bfloat16) for k in z.files if k.startswith("w::")}
