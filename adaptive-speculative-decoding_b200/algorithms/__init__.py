@@ -2,5 +2,7 @@
 from .dp_solver import (AdaptiveStopping, DynamicProgrammingSolver, OptimalStoppingTable, bayesian_adjustment,
                         compute_expected_cost, optimal_stopping_rule)
 
-__all__ = ["optimal_stopping_rule", "compute_expected_cost", "bayesian_adjustment", "OptimalStoppingTable",
+from .optimizer import GridSearchOptimizer, LambdaOptimizer, OptimizationResult, find_optimal_lambda
+
+__all__ = ["LambdaOptimizer", "GridSearchOptimizer", "OptimizationResult", "find_optimal_lambda", "optimal_stopping_rule", "compute_expected_cost", "bayesian_adjustment", "OptimalStoppingTable",
            "AdaptiveStopping", "DynamicProgrammingSolver"]

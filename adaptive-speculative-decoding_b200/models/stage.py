@@ -248,6 +248,23 @@ class StageManager:
     def stage_names(self) -> List[str]:
         return list(self.order)
 
+    def calibrate_costs(self, prompts: Optional[List[str]] = None, max_tokens: int = 32) -> Dict[str, float]:
+        """SURVEY.md 8 f3 (RealModelPipeline._calibrate_costs, real_model_pipeline.py:313-362): replace the
+        hard-coded cost table by measured per-token generation time on this machine, normalised so that the
+        first stage costs 1.0; updates ``stage.cost_per_token`` in place and returns the new table."""
+        prompts = prompts or ["Hello, how are you today?", "What is the capital of France?",
+                              "Explain machine learning in simple terms."]
+        per_tok = {}
+        for key in self.order:
+            st = self.stages[key]
+            st.generate(prompts[:1], max_tokens=4, temperature=0.0)          # warm-up
+            _, _, stats = st.generate(prompts, max_tokens=max_tokens, temperature=0.0)
+            per_tok[key] = stats["generation_time_ms"] / (len(prompts) * max_tokens)
+        base = per_tok[self.order[0]]
+        for key in self.order:
+            self.stages[key].cost_per_token = per_tok[key] / base
+        return {k: self.stages[k].cost_per_token for k in self.order}
+
     def warmup_all(self):
         for st in self.stages.values():
             st.generate(["warmup"], max_tokens=4, temperature=0.0)

@@ -19,7 +19,7 @@ def install_as_src():
     import importlib
     import sys
     import types
-    names = ["algorithms", "algorithms.dp_solver", "models", "models.stage", "models.predictor", "serving",
+    names = ["algorithms", "algorithms.dp_solver", "algorithms.optimizer", "models", "models.stage", "models.predictor", "serving",
              "serving.pipeline", "serving.cache_manager", "serving.real_model_pipeline", "theory",
              "theory.optimal_stopping"]
     root = sys.modules.setdefault("src", types.ModuleType("src"))

@@ -162,3 +162,47 @@ def test_install_as_src_aliases():
     from src.models.stage import Stage, StageManager  # noqa: F401
     from src.models.predictor import QualityPredictor, FeatureExtractor  # noqa: F401
     assert P2 is AdaptiveSpeculativePipeline and optimal_stopping_rule([1.0], [1.0], 5.0) == (0, [1.0, 0.0])
+
+
+def test_lambda_optimizer_follows_the_reference_search():
+    from asd_b200.algorithms.optimizer import GridSearchOptimizer, LambdaOptimizer, find_optimal_lambda
+    # latency falls and quality falls as lambda grows (cheaper stages chosen): bisection finds the boundary
+    ev = lambda lam: (1000.0 / (1.0 + lam), 1.0 / (1.0 + 0.1 * lam))
+    r = LambdaOptimizer(latency_constraint=100.0, lambda_bounds=(0.01, 100.0)).optimize_for_latency_constraint(ev)
+    assert r.constraint_satisfied and abs(r.optimal_lambda - 9.0) < 0.01 and r.iterations <= 50
+    with pytest.raises(ValueError):
+        LambdaOptimizer().optimize_for_latency_constraint(ev)
+    front = LambdaOptimizer().optimize_pareto_front(ev, num_points=8)
+    assert len(front) == 8 and all(front[i][1] <= front[i + 1][1] for i in range(7))
+    b = LambdaOptimizer(lambda_bounds=(0.01, 10.0)).find_balanced_lambda(ev, quality_weight=0.5)
+    assert 0.01 <= b.optimal_lambda <= 10.0
+    mgr = FakeManager(("7b", "32b"), (1.0, 4.5))
+    pipe = AdaptiveSpeculativePipeline(mgr, SeqPredictor([0.9]), None, PipelineConfig(enable_caching=False))
+    lam = find_optimal_lambda(pipe, ["a b c", "d e f"], "latency", 1e9, num_evaluations=2)
+    assert 0.01 <= lam <= 100.0 and pipe.lambda_value > 0
+    g = GridSearchOptimizer([0.5, 5.0]).search(pipe, [{"prompt": "x y"}])
+    assert g["best_lambda"] in (0.5, 5.0) and set(g["results"]) == {0.5, 5.0}
+    pipe.shutdown()
+
+
+def test_training_feature_vector_matches_the_reference_layout(tmp_path):
+    from asd_b200.training.generate_training_data import TrainingSample, extract_features, save_training_data
+    meta = {"logprobs": [-0.5, -1.5, -0.25, -2.0], "generation_time": 0.5, "completion_tokens": 4}
+    f = extract_features("how does import x work = ?", "it works it works", meta, 2)
+    assert len(f) == 64
+    lp = np.array(meta["logprobs"])
+    np.testing.assert_allclose(f[:11], [7, 26, 4, 17, 4 / 7, lp.mean(), lp.std(), lp.min(), np.percentile(lp, 25),
+                                        np.median(lp), 0.5])
+    assert f[11:15] == [0.0, 0.0, 1.0, 0.0] and f[15] == 8.0 and f[16:19] == [1.0, 1.0, 1.0] and f[22:] == [0.0] * 42
+    fused = np.array([[1, 0.5, 0.3, 1.2, 0, 0], [1, 0.9, 0.8, 0.3, 0, 0]], np.float32)
+    g = extract_features("a", "b", dict(meta, fused=fused), 0)
+    np.testing.assert_allclose(g[19:23], [0.75, 0.7, 0.55, -2.0], rtol=1e-6)
+    s = TrainingSample("p", 0, "o", "r", f, 1.0, 0.8, 0.1, 3, 4)
+    path = save_training_data([s, s], str(tmp_path))
+    import json
+    rows = json.load(open(path))
+    assert len(rows) == 2 and set(rows[0]) == {"prompt", "stage_id", "model_output", "reference_output", "features",
+                                              "quality_score", "bleu_score", "generation_time", "prompt_tokens",
+                                              "completion_tokens"}
+    stats = json.load(open(tmp_path / "feature_stats.json"))
+    assert set(stats) == {"mean", "std", "min", "max"} and len(stats["mean"]) == 64
