@@ -287,6 +287,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             PROF(PROF_ATTN);
             if (launch_attention(A, s)) return -1;
         }
+        g_gemm_prefetch_next = 1;   // the O projection follows attention, which leaves HBM mostly idle
         if (project_residual(P->o, L.t_o, P->x_attn, L.ln2)) return -1;
         {
             PROF(PROF_GEMM);
@@ -515,6 +516,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
     else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
+    else if (!strcmp(name, "l2_prefetch")) g_gemm_l2_prefetch = value;
     else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;
     else if (!strcmp(name, "profile")) {
         e->profile = value;

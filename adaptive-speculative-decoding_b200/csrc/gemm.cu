@@ -47,6 +47,7 @@ struct GemmArgs {
     uint32_t tmem_cols;
     int reduce;         // 1: the K splits of a tile form a cluster and reduce through DSMEM
     int accumulate;     // fp32 output is added to what is already there (fused residual add)
+    int l2_prefetch;    // k-blocks of weights (beyond the smem ring) each CTA pulls into L2 before the PDL wait
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
     NormFusion norm;
 };
@@ -104,6 +105,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
             const int nprod = a.stages < 4 ? a.stages : 4;
             const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
             bool waited = false;
+            // L2 prefetch of this CTA's later weight tiles: free HBM bandwidth while the upstream kernel
+            // (attention, a floor-bound small GEMM) is still running; the ring loads below then hit L2
+            {
+                const int lim = nkb < a.stages + a.l2_prefetch ? nkb : a.stages + a.l2_prefetch;
+                for (int kb = a.stages + pidx; kb < lim; kb += nprod)
+                    tma_prefetch_l2_2d(&tmap_w, (kb0 + kb) * kBlockK, tile_n * kTileN);
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % a.stages, round = kb / a.stages;
                 if (s % nprod != pidx) continue;
@@ -420,6 +428,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
     return 0;
 }
 
+int g_gemm_l2_prefetch = 0;     // k-blocks per CTA (engine option "l2_prefetch"); applied to a launch only when
+int g_gemm_prefetch_next = 0;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static int g_gemm_attr_set = 0;
@@ -532,6 +542,8 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.tmem_cols = pl.tmem_cols;
     a.reduce = pl.reduce;
     a.accumulate = accumulate ? 1 : 0;
+    a.l2_prefetch = (pdl && g_gemm_prefetch_next) ? g_gemm_l2_prefetch : 0;
+    g_gemm_prefetch_next = 0;
     a.norm = norm ? *norm : NormFusion{};
     if (a.norm.sumsq_out != nullptr) {
         if (!pl.reduce || pl.ksplit < 4 || pl.mode != GEMM_OUT_F32)

@@ -65,6 +65,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst_smem, const void* tma
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// pull a tile into L2 only (no shared-memory destination, no barrier): used to stream a GEMM's weights into
+// the 126 MB L2 while the upstream, latency-bound kernel is still running (programmatic dependent launch)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

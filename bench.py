@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.03)
 
     def summary(self):
         if not self.rows:
@@ -96,7 +96,7 @@ def run_reference(args):
     oracle.build()
     cores = os.cpu_count()
     vals = []
-    for _ in range(max(1, min(args.steps, 2))):
+    for _ in range(2 if args.steps > 1 else 1):
         r = spec_step_baseline(wl["target"], wl["draft"], wl["B"], wl["k"], wl["prefix"], wl["T"], sample_layers=1,
                                threads=cores)
         vals.append(r)
@@ -273,7 +273,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="32b", choices=["32b", "72b"])
