@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     }
 }
 
+int g_attn_wide = 0;
+
 template <int HD, int KW, int NS>
 static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
@@ -455,7 +457,8 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     const int rows = L.max_qlen * G;
     const int rg = (rows + 15) / 16;
     if (rg > 8) return set_error("attention: q_len * group = %d rows exceeds 128; chunk the query", rows);
-    const int kg = rg == 1 ? 4 : (rg == 2 ? 2 : 1);
+    // key groups per row group: keep 4-8 warps per CTA so that one CTA per SM still hides latency
+    const int kg = g_attn_wide ? (rg <= 2 ? 4 : (rg <= 4 ? 2 : 1)) : (rg == 1 ? 4 : (rg == 2 ? 2 : 1));
     const int warps = rg * kg;
     AttnArgs a;
     a.q = L.q;

@@ -515,6 +515,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "attn_target_ctas")) e->attn_target_ctas = value;
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
+    else if (!strcmp(name, "attn_wide")) g_attn_wide = value;
     else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
     else if (!strcmp(name, "l2_prefetch")) g_gemm_l2_prefetch = value;
     else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;
