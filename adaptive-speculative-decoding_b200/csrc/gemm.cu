@@ -47,14 +47,27 @@ struct GemmArgs {
     uint32_t tmem_cols;
     int reduce;         // 1: the K splits of a tile form a cluster and reduce through DSMEM
     int accumulate;     // fp32 output is added to what is already there (fused residual add)
+    int early_trigger;  // issue griddepcontrol.launch_dependents at kernel start instead of after the main loop
+    int resid_prefetch; // owner loads the old residual before the cluster barriers
     int l2_prefetch;    // k-blocks of weights (beyond the smem ring) each CTA pulls into L2 before the PDL wait
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
     NormFusion norm;
+    unsigned long long* trace;  // diagnostics: kTraceSlots globaltimer stamps per CTA (nullptr = off)
 };
 
-__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+constexpr int kTraceSlots = 16;
+__device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
+    if (a.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        a.trace[(size_t)cta * kTraceSlots + slot] = t;
+    }
+}
 
-__global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_w,
+__device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
+
+__global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                                 const __grid_constant__ CUtensorMap tmap_x,
                                                                 const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -71,6 +84,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_n = blockIdx.x, split = blockIdx.y, tile_m = blockIdx.z;
+    if (threadIdx.x == 0) {
+        trace_stamp(a, 0);
+        if (a.trace) {
+            unsigned sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            a.trace[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * kTraceSlots + 9] = sm;
+        }
+    }
     const int base = a.kblocks / a.ksplit, rem = a.kblocks % a.ksplit;
     const int kb0 = split * base + (split < rem ? split : rem);
     const int nkb = base + (split < rem ? 1 : 0);
@@ -94,6 +115,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) trace_stamp(a, 1);
+    // early trigger: the dependent grid becomes schedulable once every CTA of this grid is resident, so its
+    // weight stream fills the SMs that this grid's tail leaves idle (it still waits before reading our output)
+    if (a.early_trigger) grid_dep_launch();
 
     if (warp >= 2) {
         // ------------------------------------------------------------------ TMA producers
@@ -123,6 +148,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
                 if (!waited) {
                     grid_dep_wait();
                     waited = true;
+                    if (pidx == 0) trace_stamp(a, 2);
                 }
                 tma_load_2d_hint(st + kABytes, &tmap_x, (kb0 + kb) * kBlockK, tile_m * a.MT, &full_bar[s], pol_x);
             }
@@ -152,6 +178,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             if (lane == 0) {
+                if (kb == 0) trace_stamp(a, 3);
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + kABytes);
 #pragma unroll
@@ -174,6 +201,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         const int m0 = tile_m * a.MT;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) trace_stamp(a, 4);
         grid_dep_wait();     // (already satisfied) makes the upstream grid's writes to `out` visible here
         grid_dep_launch();
         const bool scale = a.norm.sumsq_in != nullptr;
@@ -182,9 +210,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         if (a.reduce) {
             // handled below by the whole cluster
         } else if (a.mode == GEMM_OUT_SWIGLU) {
-            // rows 0..63 = gate, 64..127 = up of ff index tile_n*64 + (row & 63)
+            // rows 0..63 = gate, 64..127 = up of ff index tile_n*64 + (row & 63).  The accumulator tile is
+            // transposed through the (now idle) tile ring as T[token][row]; then each thread combines 8
+            // consecutive ff rows of one token and writes them with one 16-byte store.  Rolled loops: see the
+            // note on instruction-cache misses in the cluster epilogue below.
+            float* T = reinterpret_cast<float*>(smem);
             const int et = threadIdx.x - 64;      // 0..127 among epilogue threads
             __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+#pragma unroll 1
             for (int c0 = 0; c0 < a.MT; c0 += 32) {
                 uint32_t r[32];
                 if (nkb > 0) {
@@ -194,25 +227,39 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = 0;
                 }
-                float* dst = xbuf + (row >> 6) * (64 * 33) + (row & 63) * 33;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(r[i]);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                // thread et: ff row (et & 63), column half (et >> 6)
-                const int fr = et & 63, ch = (et >> 6) * 16;
-                const int j = tile_n * 64 + fr;
-                const float* g = xbuf + fr * 33 + ch;
-                const float* u = xbuf + 64 * 33 + fr * 33 + ch;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int m = m0 + c0 + ch + i;
-                    if (c0 + ch + i < a.MT && m < a.M && j < a.n_valid) {
-                        const float rs = scale ? rstd_s[c0 + ch + i] : 1.0f;
-                        out[(size_t)m * a.ldo + j] = __float2bfloat16(silu_mul(g[i] * rs, u[i] * rs));
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < a.MT) T[(c0 + i) * kTileN + row] = __uint_as_float(r[i]);
             }
+            if (threadIdx.x == 64) trace_stamp(a, 5);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool wide = (a.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+#pragma unroll 1
+            for (int g = et; g < a.MT * 8; g += 128) {
+                const int col = g >> 3, f8 = (g & 7) * 8;
+                const int m = m0 + col, j0 = tile_n * 64 + f8;
+                if (m >= a.M || j0 >= a.n_valid) continue;
+                const float rs = scale ? rstd_s[col] : 1.0f;
+                const float4* tp = reinterpret_cast<const float4*>(T + col * kTileN + f8);
+                const float4 g0 = tp[0], g1 = tp[1], u0 = tp[16], u1 = tp[17];
+                float v[8];
+                v[0] = silu_mul(g0.x * rs, u0.x * rs), v[1] = silu_mul(g0.y * rs, u0.y * rs);
+                v[2] = silu_mul(g0.z * rs, u0.z * rs), v[3] = silu_mul(g0.w * rs, u0.w * rs);
+                v[4] = silu_mul(g1.x * rs, u1.x * rs), v[5] = silu_mul(g1.y * rs, u1.y * rs);
+                v[6] = silu_mul(g1.z * rs, u1.z * rs), v[7] = silu_mul(g1.w * rs, u1.w * rs);
+                __nv_bfloat16* o = out + (size_t)m * a.ldo + j0;
+                if (wide && j0 + 8 <= a.n_valid) {
+                    __nv_bfloat162 p[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (j0 + i < a.n_valid) o[i] = __float2bfloat16(v[i]);
+                }
+            }
+            if (threadIdx.x == 64) trace_stamp(a, 10);
         } else {
             const int n = tile_n * kTileN + row;
             for (int c0 = 0; c0 < a.MT; c0 += 32) {
@@ -254,18 +301,82 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
         // CTA r of the cluster owns accumulator rows [r*rows_per, (r+1)*rows_per); every CTA sends
         // those rows of its partial tile into the owner's (now idle) smem ring through DSMEM, the
         // owner adds the ksplit contributions in rank order and writes the final values once.
+        // The owner loops below are kept rolled and 128-bit wide on purpose: every CTA runs them exactly
+        // once, so straight-line unrolled code is paid for in instruction-cache misses, not saved.
         const int ks = a.ksplit, rows_per = (kTileN + ks - 1) / ks;
         const uint32_t my_rank = cluster_ctarank();
+        const bool qkv = a.mode == GEMM_OUT_QKV;
+        const int hd = qkv ? a.qkv.hd : kTileN, half = hd >> 1, pp = half / ks;
+        const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads (warps 2..5)
+        const int m0 = tile_m * a.MT;
+        float* const outf = static_cast<float*>(a.out);
+        // fp32 owner, vector form: rows_per = 4 G, G a power of two; a thread keeps its 4 output columns
+        // n .. n+3 and walks the token rows 128 / G at a time
+        const bool vec = !qkv && (ks == 2 || ks == 4 || ks == 8) && ((a.ldo | a.n_valid) & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+        const int lgG = 29 - __clz(rows_per), G = 1 << lgG;            // log2(rows_per / 4)
+        const int vq = et & (G - 1), vcstep = kTileN >> lgG;
+        const int vn = tile_n * kTileN + (int)my_rank * rows_per + 4 * vq;
+        const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees ks >= 4 in this mode
+        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lw[4] = {0.f, 0.f, 0.f, 0.f};
+        // QKV owner: a thread keeps 4 consecutive rotary pairs of one head and walks the token rows
+        const int heads_per_tile = kTileN / hd;
+        const int lgP = qkv ? 31 - __clz(heads_per_tile * pp) - 2 : 0;  // log2(pair groups per token)
+        const int ppg = pp >> 2;                                        // pair groups per head
+        const int qh2 = (et & ((1 << lgP) - 1)) / (ppg > 0 ? ppg : 1);
+        const int qpq = ((et & ((1 << lgP) - 1)) - qh2 * ppg) * 4;
+        const int qhead = tile_n * heads_per_tile + qh2;                // q heads, then k heads, then v heads
+        const int qi = (int)my_rank * pp + qpq;                         // first dim index of the 4 pairs
+        int* const kvrow = reinterpret_cast<int*>(xbuf);                // [MT] cache row of each token (kv head 0)
+        float qb1[4] = {0.f, 0.f, 0.f, 0.f}, qb2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (warp >= 2) {
+            // operands that do not depend on this GEMM are fetched before the cluster barriers
+            if (vec) {
+                const int m = m0 + (et >> lgG);
+                if (vn < a.n_valid) {
+                    if (a.accumulate && m < a.M && et < (a.MT << lgG))
+                        old = *reinterpret_cast<const float4*>(outf + (size_t)m * a.ldo + vn);
+                    if (emit) {
+                        const uint2 w4 = *reinterpret_cast<const uint2*>(a.norm.ln_w + vn);
+                        const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4.x));
+                        const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4.y));
+                        lw[0] = w01.x, lw[1] = w01.y, lw[2] = w23.x, lw[3] = w23.y;
+                    }
+                }
+            } else if (qkv) {
+                const QkvEpilogue& e = a.qkv;
+                if (qhead < e.nh + 2 * e.nkv) {
+                    const uint2 b1 = *reinterpret_cast<const uint2*>(e.bias + qhead * hd + qi);
+                    const uint2 b2 = *reinterpret_cast<const uint2*>(e.bias + qhead * hd + qi + half);
+                    const float2 a01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&b1.x));
+                    const float2 a23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&b1.y));
+                    const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&b2.x));
+                    const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&b2.y));
+                    qb1[0] = a01.x, qb1[1] = a01.y, qb1[2] = a23.x, qb1[3] = a23.y;
+                    qb2[0] = c01.x, qb2[1] = c01.y, qb2[2] = c23.x, qb2[3] = c23.y;
+                }
+                for (int c = et; c < a.MT; c += 128) {
+                    const int m = m0 + c;
+                    int r = 0;
+                    if (m < a.M) {
+                        const int pos = e.positions[m];
+                        const int page = e.page_table[(size_t)e.token_slot[m] * e.max_pages + pos / e.page_size];
+                        r = page * e.nkv * e.page_size + pos % e.page_size;
+                    }
+                    kvrow[c] = r;
+                }
+            }
+        }
         if (warp < 2) mbar_wait(tmem_full, 0);  // own MMAs done => nothing reads or fills the ring any more
         tc_fence_after();
         fence_proxy_async_smem();
         cluster_sync();
+        if (threadIdx.x == 64) trace_stamp(a, 5);
         // receive layout in the owner: recv[src][col][lrow] (lrow contiguous) so that the 32 lanes of a
         // warp (32 consecutive accumulator rows) write contiguous 64-128 byte runs through DSMEM
         // QKV mode keeps the two halves of every rotary pair in the same owner: within a head, pair p
         // (dims p and p + hd/2) goes to owner p / pp, pp = (hd/2) / ks pairs per owner per head.
-        const bool qkv = a.mode == GEMM_OUT_QKV;
-        const int hd = qkv ? a.qkv.hd : kTileN, half = hd >> 1, pp = half / ks;
         if (warp >= 2) {
             const int q = warp & 3, row = q * 32 + lane;
             int owner, lrow;
@@ -290,47 +401,78 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
             }
             tc_fence_before();
         }
+        if (threadIdx.x == 64) trace_stamp(a, 6);
         cluster_sync();
-        if (warp >= 2 && !qkv) {
-            const int et = threadIdx.x - 64;
+        if (threadIdx.x == 64) trace_stamp(a, 7);
+        const float* recv = reinterpret_cast<const float*>(smem);
+        const float4* recv4 = reinterpret_cast<const float4*>(smem);
+        if (warp >= 2 && vec) {
+            float* colsum = xbuf;                            // [MT] this owner's sum of squares per token
+            const int items = a.MT << lgG;
+            const bool n_ok = vn < a.n_valid;
+            int col = et >> lgG;
+#pragma unroll 1
+            for (int g = et; g < items; g += 128, col += vcstep) {
+                const int m = m0 + col;
+                float* o = outf + (size_t)m * a.ldo + vn;
+                float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.accumulate && n_ok && g + 128 < items && m + vcstep < a.M)
+                    nxt = *reinterpret_cast<const float4*>(o + (size_t)vcstep * a.ldo);
+                float4 acc = recv4[(col << lgG) + vq];
+#pragma unroll
+                for (int src = 1; src < 8; ++src)
+                    if (src < ks) {
+                        const float4 t = recv4[((src * a.MT + col) << lgG) + vq];
+                        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+                    }
+                float sq = 0.0f;
+                if (n_ok && m < a.M) {
+                    if (a.accumulate) acc.x = old.x + acc.x, acc.y = old.y + acc.y, acc.z = old.z + acc.z, acc.w = old.w + acc.w;
+                    *reinterpret_cast<float4*>(o) = acc;
+                    if (emit) {
+                        const __nv_bfloat162 p01 = __floats2bfloat162_rn(acc.x * lw[0], acc.y * lw[1]);
+                        const __nv_bfloat162 p23 = __floats2bfloat162_rn(acc.z * lw[2], acc.w * lw[3]);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&p01);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&p23);
+                        *reinterpret_cast<uint2*>(a.norm.resid_bf + (size_t)m * a.ldo + vn) = pk;
+                        sq = (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+                    }
+                }
+                if (emit) {   // the G lanes that share this token are consecutive: tree-reduce them
+                    for (int d = G >> 1; d >= 1; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+                    if (vq == 0) colsum[col] = sq;
+                }
+                old = nxt;
+            }
+        } else if (warp >= 2 && !qkv) {
+            // generic owner (any split, unaligned output): one element per thread and step
             const int first = (int)my_rank * rows_per;
             const int nrows = min(rows_per, kTileN - first);
-            const float* recv = reinterpret_cast<const float*>(smem);
-            float* out = static_cast<float*>(a.out);
-            const int m0 = tile_m * a.MT;
-            const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees rows_per <= 32 in this mode
-            float* colsum = xbuf;                            // [MT] this owner's sum of squares per token
+#pragma unroll 1
             for (int idx = et; idx < rows_per * a.MT; idx += 128) {
                 const int col = idx / rows_per, lrow = idx - col * rows_per;
                 float acc = recv[idx];
+#pragma unroll 1
                 for (int src = 1; src < ks; ++src) acc += recv[src * a.MT * rows_per + idx];
                 const int n = tile_n * kTileN + first + lrow, m = m0 + col;
-                float sq = 0.0f;
                 if (lrow < nrows && m < a.M && n < a.n_valid) {
-                    float* o = out + (size_t)m * a.ldo + n;
-                    const float v = a.accumulate ? *o + acc : acc;
-                    *o = v;
-                    if (emit) {
-                        a.norm.resid_bf[(size_t)m * a.ldo + n] = __float2bfloat16(v * __bfloat162float(a.norm.ln_w[n]));
-                        sq = v * v;
-                    }
-                }
-                if (emit) {   // the rows_per lanes that share this column are consecutive: tree-reduce them
-                    for (int d = rows_per >> 1; d >= 1; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-                    if (lrow == 0) colsum[col] = sq;
+                    float* o = outf + (size_t)m * a.ldo + n;
+                    *o = a.accumulate ? *o + acc : acc;
                 }
             }
-            if (emit) {
+        }
+        if (threadIdx.x == 64) trace_stamp(a, 10);
+        if (emit && !qkv) {
+            if (!vec) __trap();   // the host only asks for the norm producer on vectorisable shapes
+            if (warp >= 2) {
                 // owners -> rank 0 (DSMEM), rank 0 adds the ks values in rank order and publishes the tile's row
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const uint32_t g0 = mapa(smem_u32(xbuf + 256 + (int)my_rank * a.MT), 0);
-                for (int c = et; c < a.MT; c += 128) st_cluster_f32(g0 + c * 4, colsum[c]);
+                for (int c = et; c < a.MT; c += 128) st_cluster_f32(g0 + c * 4, xbuf[c]);
             }
-        }
-        if (a.norm.sumsq_out != nullptr && !qkv) {
             cluster_sync();
             if (warp >= 2 && my_rank == 0) {
-                const int et = threadIdx.x - 64, m0 = tile_m * a.MT;
                 for (int c = et; c < a.MT; c += 128) {
                     float t = 0.0f;
                     for (int r2 = 0; r2 < ks; ++r2) t += xbuf[256 + r2 * a.MT + c];
@@ -338,56 +480,67 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_ws_kernel(const __grid_cons
                 }
             }
         }
-        if (!qkv) {
-            // fp32 modes were handled above
-        } else if (warp >= 2) {
-            // bias + RoPE + q store / paged K,V append for this owner's pairs (all heads of the tile)
-            const int et = threadIdx.x - 64;
-            const float* recv = reinterpret_cast<const float*>(smem);
+        if (qkv && warp >= 2) {
+            // bias + RoPE + q store / paged K,V append: 4 rotary pairs (dims i..i+3 and i+half..) per thread and step
             const QkvEpilogue& e = a.qkv;
-            const int heads_per_tile = kTileN / hd, m0 = tile_m * a.MT;
-            const int per_col = heads_per_tile * pp;                 // pairs of one token in this CTA
-            for (int idx = et; idx < per_col * a.MT; idx += 128) {
-                const int col = idx / per_col, rem = idx - col * per_col;
-                const int h2 = rem / pp, pq = rem - h2 * pp;
+            const int items = a.MT << lgP, cstep = kTileN >> lgP;
+            const bool head_ok = qhead < e.nh + 2 * e.nkv;
+            const bool rot = qhead < e.nh + e.nkv;
+            const int l1 = (qh2 * 2) * pp + qpq, l2 = (qh2 * 2 + 1) * pp + qpq;   // multiples of 4
+            const bool scale = a.norm.sumsq_in != nullptr;
+            int col = et >> lgP;
+#pragma unroll 1
+            for (int g = et; g < items; g += 128, col += cstep) {
                 const int m = m0 + col;
-                const int head = tile_n * heads_per_tile + h2;       // q heads, then k heads, then v heads
-                if (m >= a.M || head >= e.nh + 2 * e.nkv) continue;
-                const int l1 = (h2 * 2) * pp + pq, l2 = (h2 * 2 + 1) * pp + pq;
-                float x1 = recv[col * rows_per + l1], x2 = recv[col * rows_per + l2];
-                for (int src = 1; src < ks; ++src) {
-                    x1 += recv[(src * a.MT + col) * rows_per + l1];
-                    x2 += recv[(src * a.MT + col) * rows_per + l2];
+                if (m >= a.M || !head_ok) continue;
+                float4 c01 = make_float4(1.f, 0.f, 1.f, 0.f), c23 = c01;          // (cos, sin) pairs
+                if (rot) {
+                    const float4* cs4 = reinterpret_cast<const float4*>(e.cs + (size_t)m * half + qi);
+                    c01 = cs4[0];
+                    c23 = cs4[1];
                 }
-                const int i = (int)my_rank * pp + pq;                // dim index of the pair, 0 .. hd/2
-                if (a.norm.sumsq_in != nullptr) {
-                    x1 *= rstd_s[col];
-                    x2 *= rstd_s[col];
+                float4 x1 = recv4[(col * rows_per + l1) >> 2], x2 = recv4[(col * rows_per + l2) >> 2];
+#pragma unroll
+                for (int src = 1; src < 8; ++src)
+                    if (src < ks) {
+                        const float4 t1 = recv4[((src * a.MT + col) * rows_per + l1) >> 2];
+                        const float4 t2 = recv4[((src * a.MT + col) * rows_per + l2) >> 2];
+                        x1.x += t1.x, x1.y += t1.y, x1.z += t1.z, x1.w += t1.w;
+                        x2.x += t2.x, x2.y += t2.y, x2.z += t2.z, x2.w += t2.w;
+                    }
+                if (scale) {
+                    const float rs = rstd_s[col];
+                    x1.x *= rs, x1.y *= rs, x1.z *= rs, x1.w *= rs;
+                    x2.x *= rs, x2.y *= rs, x2.z *= rs, x2.w *= rs;
                 }
-                x1 += __bfloat162float(e.bias[head * hd + i]);
-                x2 += __bfloat162float(e.bias[head * hd + i + half]);
-                float o1 = x1, o2 = x2;
-                if (head < e.nh + e.nkv) {
-                    const float2 cs = e.cs[(size_t)m * half + i];
-                    o1 = x1 * cs.x - x2 * cs.y;
-                    o2 = x2 * cs.x + x1 * cs.y;
-                }
+                x1.x += qb1[0], x1.y += qb1[1], x1.z += qb1[2], x1.w += qb1[3];
+                x2.x += qb2[0], x2.y += qb2[1], x2.z += qb2[2], x2.w += qb2[3];
+                // o1 = x1 cos - x2 sin, o2 = x2 cos + x1 sin (cos = 1, sin = 0 for the V heads)
+                const __nv_bfloat162 lo01 = __floats2bfloat162_rn(x1.x * c01.x - x2.x * c01.y, x1.y * c01.z - x2.y * c01.w);
+                const __nv_bfloat162 lo23 = __floats2bfloat162_rn(x1.z * c23.x - x2.z * c23.y, x1.w * c23.z - x2.w * c23.w);
+                const __nv_bfloat162 hi01 = __floats2bfloat162_rn(x2.x * c01.x + x1.x * c01.y, x2.y * c01.z + x1.y * c01.w);
+                const __nv_bfloat162 hi23 = __floats2bfloat162_rn(x2.z * c23.x + x1.z * c23.y, x2.w * c23.z + x1.w * c23.w);
                 __nv_bfloat16* dstp;
-                if (head < e.nh) {
-                    dstp = e.q_out + ((size_t)m * e.nh + head) * hd;
+                if (qhead < e.nh) {
+                    dstp = e.q_out + ((size_t)m * e.nh + qhead) * hd;
                 } else {
-                    const int pos = e.positions[m];
-                    const int page = e.page_table[(size_t)e.token_slot[m] * e.max_pages + pos / e.page_size];
-                    const int g = head < e.nh + e.nkv ? head - e.nh : head - e.nh - e.nkv;
-                    __nv_bfloat16* cache = head < e.nh + e.nkv ? e.k_cache : e.v_cache;
-                    dstp = cache + (((size_t)page * e.nkv + g) * e.page_size + pos % e.page_size) * hd;
+                    const int kvh = rot ? qhead - e.nh : qhead - e.nh - e.nkv;
+                    __nv_bfloat16* cache = rot ? e.k_cache : e.v_cache;
+                    dstp = cache + (size_t)(kvrow[col] + kvh * e.page_size) * hd;
                 }
-                dstp[i] = __float2bfloat16(o1);
-                dstp[i + half] = __float2bfloat16(o2);
+                uint2 lo, hi;
+                lo.x = *reinterpret_cast<const uint32_t*>(&lo01);
+                lo.y = *reinterpret_cast<const uint32_t*>(&lo23);
+                hi.x = *reinterpret_cast<const uint32_t*>(&hi01);
+                hi.y = *reinterpret_cast<const uint32_t*>(&hi23);
+                *reinterpret_cast<uint2*>(dstp + qi) = lo;
+                *reinterpret_cast<uint2*>(dstp + qi + half) = hi;
             }
+            if (threadIdx.x == 64) trace_stamp(a, 11);
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(a, 8);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);
@@ -429,7 +582,12 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 }
 
 int g_gemm_l2_prefetch = 0;     // k-blocks per CTA (engine option "l2_prefetch"); applied to a launch only when
-int g_gemm_prefetch_next = 0;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
+int g_gemm_prefetch_next = 0;
+int g_gemm_resid_prefetch = 1;
+int g_gemm_early_trigger = 0;
+unsigned long long* g_gemm_trace = nullptr;   // diagnostics buffer [max launches][kTraceCtas][kTraceSlots]
+int g_gemm_trace_max = 0, g_gemm_trace_next = 0;
+constexpr int kTraceCtas = 1024;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static int g_gemm_attr_set = 0;
@@ -466,7 +624,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     pl->kblocks = (K + kBlockK - 1) / kBlockK;
     const int stage_bytes = kABytes + pl->MT * 128;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + pl->MT * 4 /*rstd*/ +
-                      (mode == GEMM_OUT_SWIGLU ? 2 * 64 * 33 * 4 : (mode == GEMM_OUT_F32 ? (256 + 8 * pl->MT) * 4 : 0));
+                      (mode == GEMM_OUT_F32 ? (256 + 8 * pl->MT) * 4 : (mode == GEMM_OUT_QKV ? pl->MT * 4 : 0));
     const int max_ctas_per_sm = pl->MT <= 128 ? 3 : 2;   // TMEM: 128 / 256 columns per CTA
     const int tiles = pl->n_tiles * pl->m_tiles;
     // Split choice.  Measured on B200: one SM cannot ingest more than ~40 GB/s from HBM however deep its
@@ -505,6 +663,8 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
         const int recv = ksplit * rows_per * pl->MT * 4;
         while (stages * stage_bytes < recv) ++stages;   // the receive buffer overlays the tile ring
     }
+    if (mode == GEMM_OUT_SWIGLU)
+        while (stages * stage_bytes < pl->MT * kTileN * 4) ++stages;   // the SwiGLU transpose overlays the tile ring
     if ((mode == GEMM_OUT_SWIGLU || mode == GEMM_OUT_BF16) && ksplit != 1)
         return set_error("gemm: bf16 / SwiGLU epilogues need ksplit == 1");
     if (ksplit > pl->kblocks) ksplit = pl->kblocks;
@@ -542,13 +702,23 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.tmem_cols = pl.tmem_cols;
     a.reduce = pl.reduce;
     a.accumulate = accumulate ? 1 : 0;
+    a.resid_prefetch = g_gemm_resid_prefetch;
+    a.early_trigger = g_gemm_early_trigger;
     a.l2_prefetch = (pdl && g_gemm_prefetch_next) ? g_gemm_l2_prefetch : 0;
     g_gemm_prefetch_next = 0;
     a.norm = norm ? *norm : NormFusion{};
+    a.trace = nullptr;
+    if (g_gemm_trace && g_gemm_trace_next < g_gemm_trace_max) {
+        a.trace = g_gemm_trace + (size_t)g_gemm_trace_next * kTraceCtas * kTraceSlots;
+        if (pl.n_tiles * pl.ksplit * pl.m_tiles > kTraceCtas) a.trace = nullptr;
+        ++g_gemm_trace_next;
+    }
     if (a.norm.sumsq_out != nullptr) {
         if (!pl.reduce || pl.ksplit < 4 || pl.mode != GEMM_OUT_F32)
             return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction with ksplit >= 4");
         if (!a.norm.resid_bf || !a.norm.ln_w) return set_error("gemm: fused norm producer needs resid_bf and ln_w");
+        if (((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || (pl.ksplit & (pl.ksplit - 1)))
+            return set_error("gemm: fused norm producer needs 16-byte aligned rows and a power-of-two split");
     }
     a.qkv = QkvEpilogue{};
     if (pl.mode == GEMM_OUT_QKV) {
@@ -613,4 +783,10 @@ extern "C" int asd_linear_plan(int M, int N, int K, int out_mode, int* ksplit, i
     if (stages) *stages = pl.stages;
     if (token_tile) *token_tile = pl.MT;
     return 0;
+}
+extern "C" ASD_API int asd_debug_gemm_trace(unsigned long long* buf, int max_launches) {
+    asd::g_gemm_trace = buf;
+    asd::g_gemm_trace_max = buf ? max_launches : 0;
+    asd::g_gemm_trace_next = 0;
+    return asd::kTraceCtas * asd::kTraceSlots;
 }

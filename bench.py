@@ -133,8 +133,10 @@ def run_ours(args):
 
     t0 = time.time()
     target = QwenEngine(wl["target"], max_seqs=B, max_seq_len=max_len, max_tokens=max(256, B * (k + 1)),
-                        tp_rank=rank if world > 1 else 0, tp_size=world, device=dev).load_random(seed=1)
-    draft = QwenEngine(wl["draft"], max_seqs=B, max_seq_len=max_len, max_tokens=256, device=dev).load_random(seed=0)
+                        tp_rank=rank if world > 1 else 0, tp_size=world, device=dev,
+                        fuse_norm=not args.no_fuse_norm).load_random(seed=1)
+    draft = QwenEngine(wl["draft"], max_seqs=B, max_seq_len=max_len, max_tokens=256, device=dev,
+                       fuse_norm=not args.no_fuse_norm).load_random(seed=0)
     comm = None
     if world > 1:
         comm = NcclComm(rank, world)
@@ -286,6 +288,7 @@ def main():
     ap.add_argument("--temperature", type=float, default=0.7)
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse-norm", action="store_true", help="separate add+RMSNorm kernels instead of the fused epilogues")
     ap.add_argument("--nccl-only", action="store_true", help="TP boundaries through ncclAllReduce instead of the fused kernel")
     ap.add_argument("--opt", action="append", help="engine option name=value (e.g. pdl=0, attn_impl=0)")
     args = ap.parse_args()

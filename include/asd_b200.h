@@ -159,6 +159,11 @@ ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
  * this call synchronises and returns the summed milliseconds and launch counts by kernel class
  * {0 weight-streaming GEMMs, 1 attention, 2 glue (norm/rope/gather), 3 TP all-reduce, 4 lm_head GEMM}
  * since the previous read (bench.py's roofline numbers come from here). nclass >= 5. */
+/* Diagnostics: every following GEMM launch (up to max_launches, <= 1024 CTAs each) records per-CTA globaltimer
+ * stamps into buf (device, u64): {entry, setup done, upstream grid done, first tile landed, main loop done,
+ * cluster barrier 1, scatter done, cluster barrier 2, exit, smid}.  Returns the u64 stride per launch; buf = NULL
+ * switches tracing off. */
+ASD_API int asd_debug_gemm_trace(unsigned long long* buf, int max_launches);
 ASD_API int asd_engine_profile_read(asd_engine_t* e, float* ms_by_class, int* launches_by_class, int nclass);
 /*
  * One forward pass over M tokens (draft step: q_len 1; verify step: q_len k+1; prefill chunk).
