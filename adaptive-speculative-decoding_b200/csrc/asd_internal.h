@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define ASD_NUM_FEATURES 6
 
@@ -17,6 +18,19 @@ void count_launch(int n);
         if (_e != cudaSuccess)                                                                \
             return ::asd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+// Every kernel of a forward pass asks for the same (maximum) shared-memory carve-out: an SM only re-partitions
+// L1/shared memory when it is idle, so kernels with different carve-outs cannot be co-resident and a
+// programmatically launched GEMM could not start streaming weights next to the attention CTAs.
+// ASD_CARVEOUT=0 in the environment leaves the driver's per-kernel choice (for A/B runs).
+template <typename F>
+inline void prefer_max_smem(F* fn) {
+    static const bool on = []() {
+        const char* v = getenv("ASD_CARVEOUT");
+        return !(v && v[0] == '0');
+    }();
+    if (on) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 // sampler.cu
 size_t reject_sample_workspace_bytes(int B, int k);

@@ -425,6 +425,7 @@ static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cu
     if (!attr_set) {
         ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<HD, KW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
+        prefer_max_smem(attn_mma_kernel<HD, KW, NS>);
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};

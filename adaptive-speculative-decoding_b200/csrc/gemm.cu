@@ -585,6 +585,7 @@ int g_gemm_l2_prefetch = 0;     // k-blocks per CTA (engine option "l2_prefetch"
 int g_gemm_prefetch_next = 0;
 int g_gemm_resid_prefetch = 1;
 int g_gemm_early_trigger = 0;
+int g_gemm_headroom = 1;
 unsigned long long* g_gemm_trace = nullptr;   // diagnostics buffer [max launches][kTraceCtas][kTraceSlots]
 int g_gemm_trace_max = 0, g_gemm_trace_next = 0;
 constexpr int kTraceCtas = 1024;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
@@ -652,7 +653,10 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     int ctas_per_sm = (tiles * ksplit + g_num_sms - 1) / g_num_sms;
     if (ctas_per_sm > max_ctas_per_sm) ctas_per_sm = max_ctas_per_sm;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const int budget = (225 * 1024) / ctas_per_sm - fixed - 1024;
+    // headroom: leave shared memory for that many CTAs of the NEXT kernel (programmatic launch + early trigger)
+    // (measured: pays for the draft's 16-token tiles, whose rings stay >= 4 deep; costs the verify tiles a stage)
+    const int headroom = pl->MT <= 32 ? g_gemm_headroom : 0;
+    const int budget = (225 * 1024) / (ctas_per_sm + headroom) - fixed - 1024;
     int stages = budget / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -685,6 +689,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     if (!g_gemm_attr_set) {
         if (device_props()) return -1;
         ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+        prefer_max_smem(gemm_ws_kernel);
         g_gemm_attr_set = 1;
     }
     GemmArgs a;

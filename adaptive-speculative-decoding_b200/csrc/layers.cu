@@ -16,7 +16,8 @@
 
 namespace asd {
 
-int g_glue_pdl = 1;   // launch the glue kernels programmatically (they wait on griddepcontrol)
+int g_glue_pdl = 1;
+static void glue_carveout();   // same shared-memory carve-out for every glue kernel (see prefer_max_smem)   // launch the glue kernels programmatically (they wait on griddepcontrol)
 
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxVec = 8;  // float4 per thread -> hidden <= 8192
@@ -111,6 +112,7 @@ int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_s
                     cudaStream_t stream, __nv_bfloat16* resid_bf, float* sumsq0) {
     if (h % 4 || h > kNormThreads * kNormMaxVec * 4) return set_error("add_norm: hidden must be %%4 and <= 8192");
     if (M <= 0) return 0;
+    glue_carveout();
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -238,6 +240,7 @@ int launch_tp_allreduce_norm(const float* const* peer_bufs, uint32_t* const* pee
     tp.world = world;
     tp.epoch = epoch;
     tp.error = error;
+    glue_carveout();
     tp_allreduce_norm_kernel<<<M, kNormThreads, 0, stream>>>(tp, resid, w, xnorm, h, eps, resid_bf, sumsq0);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
@@ -353,6 +356,7 @@ __global__ void rope_table_kernel(const int* __restrict__ positions, const float
 
 int launch_rope_table(const int* positions, const float* inv_freq, float2* cs, int M, int half, cudaStream_t stream) {
     if (M <= 0) return 0;
+    glue_carveout();
     rope_table_kernel<<<M, 64, 0, stream>>>(positions, inv_freq, cs, half);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
@@ -373,10 +377,23 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
 int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16* dst, int n, int h,
                        cudaStream_t stream, const float* ss_src, float* ss_dst, int parts, int ld) {
     if (n <= 0) return 0;
+    glue_carveout();
     gather_rows_kernel<<<n, 128, 0, stream>>>(src, rows, dst, h, ss_src, ss_dst, parts, ld);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
+}
+
+static void glue_carveout() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    prefer_max_smem(add_norm_kernel);
+    prefer_max_smem(tp_allreduce_norm_kernel);
+    prefer_max_smem(reduce_slices_kernel);
+    prefer_max_smem(qkv_rope_kernel);
+    prefer_max_smem(rope_table_kernel);
+    prefer_max_smem(gather_rows_kernel);
 }
 
 }  // namespace asd
