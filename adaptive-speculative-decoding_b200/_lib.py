@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
         "asd_engine_tp_error": (i32, [vp]),
         "asd_engine_profile_read": (i32, [vp, vp, vp, i32]),
         "asd_debug_gemm_trace": (i32, [vp, i32]),
+        "asd_debug_attn_trace": (i32, [vp, i32]),
         "asd_engine_forward": (i32, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, c.c_longlong, vp]),
     }
     for name, (res, args) in sigs.items():

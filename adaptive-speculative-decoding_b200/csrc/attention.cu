@@ -109,7 +109,17 @@ struct AttnArgs {
     float* ml_part;                // [M, nh, nsplit_max, 2]
     int* tickets;                  // [nseq_max * nkv], zero between launches
     __nv_bfloat16* out;            // [M, nh, hd]
+    unsigned long long* trace;     // diagnostics: 16 globaltimer stamps per CTA (nullptr = off)
 };
+
+__device__ __forceinline__ void attn_stamp(const AttnArgs& a, int slot) {
+    if (a.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        a.trace[(size_t)cta * 16 + slot] = t;
+    }
+}
 
 // HD = head_dim (64 or 128); KW = keys of each 64-key tile handled by one warp (64, 32 or 16).
 // warp w = (row group w % rg_count, key group w / rg_count): 16 query rows x KW keys per tile.
@@ -131,7 +141,10 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
 
     const int seq = blockIdx.x, g = blockIdx.y, sp = blockIdx.z;
     const int G = a.nh / a.nkv;
-    grid_dep_wait();   // q and the new K/V come from the QKV GEMM launched just before
+    attn_stamp(a, 0);
+    // Everything up to the PDL wait reads only what earlier forwards (or the host) wrote: the batch
+    // description, the page table and the K/V of keys older than this step's tokens.  The QKV GEMM that is
+    // still running upstream only produces q and the K/V of the last qlen positions.
     const int q0 = a.cu_q[seq], qlen = a.cu_q[seq + 1] - q0;
     if (qlen <= 0) return;
     const int R = qlen * G;
@@ -140,19 +153,20 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     if (kbeg >= kv_len) return;
     const int kend = min(kv_len, kbeg + a.split_keys);
     const int nsplit_seq = (kv_len + a.split_keys - 1) / a.split_keys;
-    const int slot = a.seq_slot[seq];
-    const int* pt = a.page_table + (size_t)slot * a.max_pages;
-    grid_dep_launch();
-
-    // ---- stage Q (rows r = t*G + gq -> token q0+t, head g*G+gq), swizzled
-    for (int c = threadIdx.x; c < a.rg_count * 16 * CH; c += blockDim.x) {
-        const int r = c / CH, ch = c - r * CH;
-        const bool ok = r < R;
-        const int t = ok ? r / G : 0, gq = ok ? r - t * G : 0;
-        const __nv_bfloat16* src = a.q + ((size_t)(q0 + t) * a.nh + g * G + gq) * HD + ch * 8;
-        cp_async16(uQ + r * ROWB + ((ch ^ (r & 7)) << 4), src, ok);
+    const int old_keys = kv_len - qlen;
+    // this CTA's slice of the sequence's page table, staged once (a lookup per key row would be a dependent
+    // L2 round trip in front of every cp.async batch)
+    int* s_pt = reinterpret_cast<int*>(sV + NS * kKeyTile * ROWB);
+    const int page0 = kbeg / a.page_size;
+    {
+        const int* pt = a.page_table + (size_t)a.seq_slot[seq] * a.max_pages;
+        const int npages = (kend - 1) / a.page_size - page0 + 1;
+        for (int i = threadIdx.x; i < npages; i += blockDim.x) s_pt[i] = pt[page0 + i];
     }
-    // 4 threads per key row: one page-table lookup per (thread, row), then CH/4 16-byte chunks of K and V
+    __syncthreads();
+    attn_stamp(a, 1);
+
+    // 4 threads per key row: CH/4 16-byte chunks of K and V each
     auto load_tile = [&](int tile, int buf) {
         const int j0 = kbeg + tile * kKeyTile;
         const int sub = threadIdx.x & 3;
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
             const int j = j0 + r;
             const bool ok = j < kend;
             const int jj = ok ? j : kbeg;
-            const int page = pt[jj / a.page_size];
+            const int page = s_pt[jj / a.page_size - page0];
             const size_t off = (((size_t)page * a.nkv + g) * a.page_size + jj % a.page_size) * HD;
             const uint32_t drow = (uint32_t)(buf * kKeyTile * ROWB + r * ROWB);
 #pragma unroll
@@ -173,12 +187,29 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
         }
     };
     const int ntiles = (kend - kbeg + kKeyTile - 1) / kKeyTile;
+    auto tile_is_old = [&](int t) { return kbeg + (t + 1) * kKeyTile <= old_keys; };
 #pragma unroll
-    for (int t = 0; t < NS - 1; ++t) {   // prologue: NS-1 tiles in flight (Q rides in the first group)
-        if (t < ntiles) load_tile(t, t);
-        cp_async_commit();
-    }
+    for (int t = 0; t < NS - 1; ++t)     // prologue, part 1: the old tiles among the first NS-1
+        if (t < ntiles && tile_is_old(t)) load_tile(t, t);
+    cp_async_commit();
+    attn_stamp(a, 2);
+    grid_dep_wait();   // q and the new K/V come from the QKV GEMM launched just before
+    grid_dep_launch();
 
+    // ---- stage Q (rows r = t*G + gq -> token q0+t, head g*G+gq), swizzled
+    for (int c = threadIdx.x; c < a.rg_count * 16 * CH; c += blockDim.x) {
+        const int r = c / CH, ch = c - r * CH;
+        const bool ok = r < R;
+        const int t = ok ? r / G : 0, gq = ok ? r - t * G : 0;
+        const __nv_bfloat16* src = a.q + ((size_t)(q0 + t) * a.nh + g * G + gq) * HD + ch * 8;
+        cp_async16(uQ + r * ROWB + ((ch ^ (r & 7)) << 4), src, ok);
+    }
+#pragma unroll
+    for (int t = 0; t < NS - 1; ++t)     // prologue, part 2: tiles that hold this step's keys
+        if (t < ntiles && !tile_is_old(t)) load_tile(t, t);
+    cp_async_commit();
+
+    attn_stamp(a, 3);
     const int r0 = rg * 16 + (lane >> 2), r1 = r0 + 8;
     const int qpos0 = kv_len - qlen + (r0 < R ? r0 / G : 0), qpos1 = kv_len - qlen + (r1 < R ? r1 / G : 0);
     float o[HD / 8][4];
@@ -189,10 +220,12 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
 
     for (int tile = 0; tile < ntiles; ++tile) {
         const int buf = tile % NS;
+        if (tile == 0) cp_async_wait<0>();   // the whole prologue (NS-1 tiles and Q)
         if (tile + NS - 1 < ntiles) load_tile(tile + NS - 1, (tile + NS - 1) % NS);
         cp_async_commit();
-        cp_async_wait<NS - 1>();
+        if (tile > 0) cp_async_wait<NS - 1>();
         __syncthreads();
+        if (tile == 0) attn_stamp(a, 4);
         if (tile == 0) {
             const int mi = lane >> 3;
             const int row = rg * 16 + (lane & 7) + (mi & 1) * 8;
@@ -281,6 +314,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
         __syncthreads();  // everyone done with this buffer before it is refilled
     }
     cp_async_wait<0>();
+    attn_stamp(a, 5);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -345,6 +379,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
             mx1 = m1;
         }
     }
+    attn_stamp(a, 6);
     // ---- results: final output when the sequence has a single split, else partials + last-CTA combine
     if (kg == 0) {
 #pragma unroll
@@ -378,6 +413,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
             }
         }
     }
+    attn_stamp(a, 7);
     if (nsplit_seq == 1) return;
     // the last CTA of this (sequence, kv head) to finish merges the splits (no separate combine launch)
     __threadfence();
@@ -388,6 +424,7 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
         if (s_last) a.tickets[seq * a.nkv + g] = 0;
     }
     __syncthreads();
+    attn_stamp(a, 8);
     if (!s_last) return;
     __threadfence();
     for (int idx = threadIdx.x; idx < R * (HD / 4); idx += blockDim.x) {
@@ -415,9 +452,12 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
         op[0] = __floats2bfloat162_rn(acc.x * inv, acc.y * inv);
         op[1] = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
     }
+    attn_stamp(a, 9);
 }
 
 int g_attn_wide = 0;
+unsigned long long* g_attn_trace = nullptr;
+int g_attn_trace_max = 0, g_attn_trace_next = 0;
 
 template <int HD, int KW, int NS>
 static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
@@ -482,9 +522,15 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     a.ml_part = L.ml_part;
     a.tickets = L.tickets;
     a.out = L.out;
+    a.trace = nullptr;
+    if (g_attn_trace && g_attn_trace_next < g_attn_trace_max)
+        a.trace = g_attn_trace + (size_t)(g_attn_trace_next++) * 1024 * 16;
     const dim3 grid(L.nseq, L.nkv, L.nsplit_max);
+    if (grid.x * grid.y * grid.z > 1024) a.trace = nullptr;
     const int ns = (int)(grid.x * grid.y * grid.z) <= 148 ? 4 : 2;   // one CTA per SM: deeper K/V ring
     size_t smem = (size_t)rg * 16 * L.hd * 2 + 2 * (size_t)ns * kKeyTile * L.hd * 2;
+    const size_t pt_bytes = ((size_t)L.split_keys / L.page_size + 2) * sizeof(int);   // staged page-table slice
+    smem += pt_bytes;
     const size_t merge = (size_t)rg * 16 * L.hd * 2 + (size_t)warps * 16 * (L.hd + 2) * 4;
     if (kg > 1 && merge > smem) smem = merge;
     const int kw = kKeyTile / kg, th = warps * 32;
@@ -502,3 +548,10 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
 }
 
 }  // namespace asd
+
+extern "C" __attribute__((visibility("default"))) int asd_debug_attn_trace(unsigned long long* buf, int max_launches) {
+    asd::g_attn_trace = buf;
+    asd::g_attn_trace_max = buf ? max_launches : 0;
+    asd::g_attn_trace_next = 0;
+    return 1024 * 16;
+}

@@ -59,7 +59,7 @@ struct Engine {
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     // options
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
-        attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0;
+        attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // fused peer-memory all-reduce (CUDA IPC): double-buffered partials + flag array, local and peer views
@@ -150,9 +150,11 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     const bool tp = c.tp_size > 1;
     if (tp && !e->allreduce && !e->p2p) return set_error("engine: tp_size > 1 but no all-reduce installed");
 
-    // attention split selection: fill the SMs once, >= 4 key tiles per split, bounded workspace
+    // attention split selection: fill the SMs once, bounded workspace.  A split costs a ticket plus a merge
+    // pass (~4 us, more than ten 64-key tiles of the key loop), so a sequence is only split into pieces of
+    // at least attn_min_split_keys keys
     int nsplit = (e->attn_target_ctas + nseq * nkv / 2) / (nseq * nkv);
-    const int max_by_len = max_kv_len / 256 > 0 ? max_kv_len / 256 : 1;
+    const int max_by_len = max_kv_len / e->attn_min_split_keys > 0 ? max_kv_len / e->attn_min_split_keys : 1;
     if (nsplit > max_by_len) nsplit = max_by_len;
     if (nsplit > e->max_attn_splits) nsplit = e->max_attn_splits;
     if (nsplit < 1) nsplit = 1;
@@ -513,6 +515,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "stages")) e->force_stages = value;
     else if (!strcmp(name, "reduce")) e->reduce = value;
     else if (!strcmp(name, "attn_target_ctas")) e->attn_target_ctas = value;
+    else if (!strcmp(name, "attn_min_split_keys")) e->attn_min_split_keys = value < 64 ? 64 : value;
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
     else if (!strcmp(name, "attn_wide")) g_attn_wide = value;

@@ -164,6 +164,9 @@ ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
  * cluster barrier 1, scatter done, cluster barrier 2, exit, smid}.  Returns the u64 stride per launch; buf = NULL
  * switches tracing off. */
 ASD_API int asd_debug_gemm_trace(unsigned long long* buf, int max_launches);
+/* Same for the attention kernel: {entry, upstream grid done, metadata read, loads issued, first K/V tile landed,
+ * key loop done, key groups merged, partials stored, ticket taken, exit of the merging CTA}. */
+ASD_API int asd_debug_attn_trace(unsigned long long* buf, int max_launches);
 ASD_API int asd_engine_profile_read(asd_engine_t* e, float* ms_by_class, int* launches_by_class, int nclass);
 /*
  * One forward pass over M tokens (draft step: q_len 1; verify step: q_len k+1; prefill chunk).

@@ -85,6 +85,25 @@ def test_engine_unfused_paths(opts):
     eng.close()
 
 
+@pytest.mark.parametrize("min_keys,target", [(128, 592), (64, 2000), (256, 148)])
+def test_attention_key_splits(min_keys, target):
+    """long sequences split their keys over several CTAs (flash-decoding); the last CTA merges the partials"""
+    from asd_b200.engine import QwenEngine
+    cfg = Qwen2Config(1024, 1, 8, 1, 512, 1024, head_dim=128, name="g8")
+    w = random_hf_weights(cfg, seed=11)
+    ids = torch.randint(0, cfg.vocab_size, (2, 700), generator=torch.Generator().manual_seed(5))
+    ref = qwen2_forward(w, cfg, ids)
+    eng = QwenEngine(cfg, max_seqs=2, max_seq_len=720, max_tokens=64).load_hf_weights(w)
+    eng.set_option("attn_min_split_keys", min_keys)
+    eng.set_option("attn_target_ctas", target)
+    slots = torch.arange(2, dtype=torch.int32, device="cuda")
+    idc = ids.cuda().to(torch.int32)
+    eng.prefill(idc[:, :691], slots)
+    ver = eng.forward_uniform(idc[:, 691:].contiguous(), torch.full((2,), 691, dtype=torch.int32, device="cuda"), slots, 700)
+    check(ver.view(2, 9, -1).cpu(), ref[:, 691:])
+    eng.close()
+
+
 def test_prefill_with_single_token_tail_chunk():
     """chunk sizes that leave a 1-token tail (a strided [B, 1] view of the prompt) must still be correct"""
     cfg = Qwen2Config(512, 2, 8, 2, 1024, 4096, head_dim=128, name="tail")

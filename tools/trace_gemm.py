@@ -31,10 +31,15 @@ L = _lib.lib()
 MAXL = 1000
 stride = L.asd_debug_gemm_trace(None, 0)
 buf = torch.zeros(MAXL * stride, dtype=torch.int64, device="cuda")
+abuf = torch.zeros(MAXL * 1024 * 16, dtype=torch.int64, device="cuda")
 L.asd_debug_gemm_trace(buf.data_ptr(), MAXL)
+L.asd_debug_attn_trace(abuf.data_ptr(), MAXL)
 dec.step()
 torch.cuda.synchronize()
 L.asd_debug_gemm_trace(None, 0)
+L.asd_debug_attn_trace(None, 0)
+atr = abuf.cpu().numpy().reshape(MAXL, 1024, 16)
+np.save("gpurun_out/attn_trace.npy", atr[:, :512].copy())
 tr = buf.cpu().numpy().reshape(MAXL, stride // 16, 16)
 os.makedirs("gpurun_out", exist_ok=True)
 np.save("gpurun_out/gemm_trace.npy", tr[:, :512].copy())
@@ -73,3 +78,35 @@ for which, part in (("verify", ver), ("draft", info[: 28 * 4 + 1])):
         print(f"{names[g]:8s} ctas {int(r[0]):4d} sms {int(r[1]):3d} period {r[2]:6.1f} span {r[3]:6.1f} gap_prev {r[4]:6.1f}")
         print("   median " + " ".join(f"{lab[j]} {r[5 + j]:5.1f}" for j in range(NS) if j != 9))
         print("   max    " + " ".join(f"{lab[j]} {r[5 + NS + j]:5.1f}" for j in range(NS) if j != 9))
+
+
+# ---- absolute timeline of one mid layer (GEMMs + attention), times in us from the layer's first CTA entry
+def timeline(gl, al, title):
+    print(f"== {title}")
+    ev = []
+    for i in gl:
+        x = tr[i]
+        x = x[x[:, 0] != 0].astype(np.int64)
+        ev.append(("gemm%4d" % len(x), x, [0, 2, 3, 4, 8]))
+    x = atr[al]
+    x = x[x[:, 0] != 0].astype(np.int64)
+    ev.append(("attn%4d" % len(x), x, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]))
+    ev.sort(key=lambda e: e[1][:, 0].min())
+    T0 = ev[0][1][:, 0].min()
+    for name, x, cols in ev:
+        out = []
+        for c in cols:
+            v = x[:, c][x[:, c] > 0]
+            out.append(f"s{c}: " + ("-" if len(v) == 0 else f"{np.percentile(v - T0, 10) / 1e3:6.1f}/{np.median(v - T0) / 1e3:6.1f}/{(v - T0).max() / 1e3:6.1f}"))
+        print(name, " ".join(out))
+
+
+aused = [i for i in range(MAXL) if atr[i, 0, 0] != 0]
+nd = 28
+# draft forward #2 (0-based), layer 14; verify layer 30.  Per forward: 4 GEMMs per layer (+ lm_head), 1 attention.
+ndraft_fw = (len(used) - (64 * 4 + 1)) // (nd * 4 + 1)
+g0 = used[2 * (nd * 4 + 1) + 14 * 4]
+timeline([g0 + j for j in range(5)], aused[2 * nd + 14], f"draft forward 2 layer 14 ({ndraft_fw} draft forwards)")
+vb = len(used) - (64 * 4 + 1)
+g0 = used[vb + 30 * 4]
+timeline([g0 + j for j in range(5)], aused[ndraft_fw * nd + 30], "verify layer 30")
