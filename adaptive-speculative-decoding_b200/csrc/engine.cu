@@ -524,6 +524,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "resid_prefetch")) g_gemm_resid_prefetch = value;
     else if (!strcmp(name, "early_trigger")) g_gemm_early_trigger = value;
     else if (!strcmp(name, "headroom")) g_gemm_headroom = value;
+    else if (!strcmp(name, "recv_dedicated")) g_gemm_recv_dedicated = value;
     else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;
     else if (!strcmp(name, "profile")) {
         e->profile = value;

@@ -47,6 +47,7 @@ struct GemmArgs {
     uint32_t tmem_cols;
     int reduce;         // 1: the K splits of a tile form a cluster and reduce through DSMEM
     int accumulate;     // fp32 output is added to what is already there (fused residual add)
+    int recv_dedicated; // small token tiles: the DSMEM receive buffer has its own smem, so no barrier before the scatter
     int early_trigger;  // issue griddepcontrol.launch_dependents at kernel start instead of after the main loop
     int resid_prefetch; // owner loads the old residual before the cluster barriers
     int l2_prefetch;    // k-blocks of weights (beyond the smem ring) each CTA pulls into L2 before the PDL wait
@@ -119,6 +120,9 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
     // early trigger: the dependent grid becomes schedulable once every CTA of this grid is resident, so its
     // weight stream fills the SMs that this grid's tail leaves idle (it still waits before reading our output)
     if (a.early_trigger) grid_dep_launch();
+    // phase 0 of the cluster barrier only proves that every CTA of the cluster is running (DSMEM is legal from
+    // then on); arriving here and waiting right before the scatter makes it free
+    if (a.reduce && a.recv_dedicated) cluster_arrive();
 
     if (warp >= 2) {
         // ------------------------------------------------------------------ TMA producers
@@ -370,8 +374,15 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
         }
         if (warp < 2) mbar_wait(tmem_full, 0);  // own MMAs done => nothing reads or fills the ring any more
         tc_fence_after();
-        fence_proxy_async_smem();
-        cluster_sync();
+        uint8_t* recv_base = smem;               // the receive buffer overlays the (idle) tile ring ...
+        if (a.recv_dedicated) {                  // ... or, for small token tiles, has its own shared memory
+            const int xb_floats = qkv ? a.MT : 256 + 8 * a.MT;
+            recv_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xbuf + xb_floats) + 15) & ~uintptr_t(15));
+            cluster_wait();
+        } else {
+            fence_proxy_async_smem();
+            cluster_sync();                      // every CTA of the cluster is done with its ring
+        }
         if (threadIdx.x == 64) trace_stamp(a, 5);
         // receive layout in the owner: recv[src][col][lrow] (lrow contiguous) so that the 32 lanes of a
         // warp (32 consecutive accumulator rows) write contiguous 64-128 byte runs through DSMEM
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
                 lrow = row - owner * rows_per;
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-            const uint32_t dst = mapa(smem_u32(smem) + (uint32_t)((int)my_rank * a.MT * rows_per + lrow) * 4u,
+            const uint32_t dst = mapa(smem_u32(recv_base) + (uint32_t)((int)my_rank * a.MT * rows_per + lrow) * 4u,
                                       (uint32_t)owner);
             for (int c0 = 0; c0 < a.MT; c0 += 32) {
                 uint32_t r[32];
@@ -404,8 +415,8 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
         if (threadIdx.x == 64) trace_stamp(a, 6);
         cluster_sync();
         if (threadIdx.x == 64) trace_stamp(a, 7);
-        const float* recv = reinterpret_cast<const float*>(smem);
-        const float4* recv4 = reinterpret_cast<const float4*>(smem);
+        const float* recv = reinterpret_cast<const float*>(recv_base);
+        const float4* recv4 = reinterpret_cast<const float4*>(recv_base);
         if (warp >= 2 && vec) {
             float* colsum = xbuf;                            // [MT] this owner's sum of squares per token
             const int items = a.MT << lgG;
@@ -586,6 +597,7 @@ int g_gemm_prefetch_next = 0;
 int g_gemm_resid_prefetch = 1;
 int g_gemm_early_trigger = 0;
 int g_gemm_headroom = 1;
+int g_gemm_recv_dedicated = 1;
 unsigned long long* g_gemm_trace = nullptr;   // diagnostics buffer [max launches][kTraceCtas][kTraceSlots]
 int g_gemm_trace_max = 0, g_gemm_trace_next = 0;
 constexpr int kTraceCtas = 1024;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
@@ -661,11 +673,19 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     if (force_stages > 0) stages = force_stages;
+    pl->recv_dedicated = 0;
+    int recv_extra = 0;
     if (pl->reduce && (ksplit > 1 || mode == GEMM_OUT_QKV)) {
         if (ksplit > 8) return set_error("gemm: cluster reduction supports ksplit <= 8");
         const int rows_per = (kTileN + ksplit - 1) / ksplit;
         const int recv = ksplit * rows_per * pl->MT * 4;
-        while (stages * stage_bytes < recv) ++stages;   // the receive buffer overlays the tile ring
+        if (pl->MT <= 32 && g_gemm_recv_dedicated) {
+            pl->recv_dedicated = 1;                     // small tiles: own receive buffer, one cluster barrier less
+            recv_extra = recv + 16;
+            while (stages > 2 && fixed + recv_extra + stages * stage_bytes > budget + fixed) --stages;
+        } else {
+            while (stages * stage_bytes < recv) ++stages;   // the receive buffer overlays the tile ring
+        }
     }
     if (mode == GEMM_OUT_SWIGLU)
         while (stages * stage_bytes < pl->MT * kTileN * 4) ++stages;   // the SwiGLU transpose overlays the tile ring
@@ -675,7 +695,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     pl->ksplit = ksplit;
     pl->stages = stages;
     if (ksplit == 1 && mode != GEMM_OUT_QKV) pl->reduce = 0;
-    pl->smem_bytes = fixed + stages * stage_bytes;
+    pl->smem_bytes = fixed + recv_extra + stages * stage_bytes;
     if (pl->smem_bytes > g_smem_optin) return set_error("gemm: tile does not fit in shared memory");
     uint32_t cols = 32;
     while ((int)cols < pl->MT) cols <<= 1;
@@ -706,6 +726,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.out = out;
     a.tmem_cols = pl.tmem_cols;
     a.reduce = pl.reduce;
+    a.recv_dedicated = pl.recv_dedicated;
     a.accumulate = accumulate ? 1 : 0;
     a.resid_prefetch = g_gemm_resid_prefetch;
     a.early_trigger = g_gemm_early_trigger;

@@ -37,11 +37,11 @@ struct QkvEpilogue {
 
 struct GemmPlan {
     int M, N, K, mode;
-    int MT, m_tiles, n_tiles, kblocks, ksplit, stages, smem_bytes, reduce;
+    int MT, m_tiles, n_tiles, kblocks, ksplit, stages, smem_bytes, reduce, recv_dedicated;
     uint32_t tmem_cols;
 };
 
-extern int g_gemm_l2_prefetch, g_gemm_prefetch_next, g_gemm_resid_prefetch, g_gemm_early_trigger, g_gemm_headroom;
+extern int g_gemm_l2_prefetch, g_gemm_prefetch_next, g_gemm_resid_prefetch, g_gemm_early_trigger, g_gemm_headroom, g_gemm_recv_dedicated;
 int gemm_token_tile(int M);
 // reduce = 1: the K splits of a tile form a thread-block cluster and reduce through DSMEM, so the fp32
 // output is final ([M][ldo], one slice) instead of one slice per split
