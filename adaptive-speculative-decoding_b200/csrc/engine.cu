@@ -59,7 +59,7 @@ struct Engine {
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     // options
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
-        attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024;
+        attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // fused peer-memory all-reduce (CUDA IPC): double-buffered partials + flag array, local and peer views
@@ -186,9 +186,34 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     auto project_residual = [&](const GemmPlan& pl, const CUtensorMap& tw, const CUtensorMap& tx,
                                 const __nv_bfloat16* next_ln) -> int {
         const bool fuse = !tp && (pl.reduce || pl.ksplit == 1);
-        const bool emit = fn && fuse && pl.reduce && pl.ksplit >= 4;
+        const bool pow2 = pl.ksplit >= 2 && (pl.ksplit & (pl.ksplit - 1)) == 0;
+        const bool emit = fn && fuse && pl.reduce && pow2;
         const bool p2p_ok = tp && e->p2p && (pl.reduce || pl.ksplit == 1);
         if (p2p_ok) ++e->tp_epoch;
+        if (p2p_ok && e->tp_fused && fn && pl.reduce && pow2 && pl.m_tiles * pl.n_tiles * pl.ksplit <= kTpFlagSlots) {
+            // tensor parallel, fused: the GEMM's owner CTAs exchange their partial tiles over NVLink peer memory
+            // and finish residual + norm statistics themselves - same five launches per layer as on one GPU
+            PROF(PROF_GEMM);
+            const uint32_t ep = e->tp_epoch;
+            TpFusion tf;
+            for (int r = 0; r < c.tp_size; ++r) {
+                tf.recv[r] = const_cast<float*>(e->peer_buf[ep & 1][r]);
+                tf.flags[r] = e->peer_flags[r] + 64;     // fused flags live behind the 64 words of the all-reduce kernel
+            }
+            tf.rank = c.tp_rank;
+            tf.world = c.tp_size;
+            tf.epoch = ep;
+            tf.error = e->tp_error;
+            tf.slot_stride = Mx * (size_t)h;
+            NormFusion prod;
+            prod.sumsq_out = e->sumsq;
+            prod.ld = Mx;
+            prod.resid_bf = e->resid_bf;
+            prod.ln_w = next_ln;
+            if (gemm_launch(pl, tw, tx, e->resid, h, h, e->pdl, s, true, nullptr, &prod, &tf)) return -1;
+            parts = pl.n_tiles;
+            return 0;
+        }
         NormFusion prod;
         if (emit) {
             prod.sumsq_out = e->sumsq;
@@ -375,12 +400,15 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
     alloc((void**)&e->tickets, Mx * c.n_kv_heads * 4);
     if (ok && cudaMemset(e->tickets, 0, Mx * c.n_kv_heads * 4) != cudaSuccess) ok = false;
     if (c.tp_size > 1) {
-        alloc((void**)&e->tp_buf[0], Mx * c.hidden * 4);
-        alloc((void**)&e->tp_buf[1], Mx * c.hidden * 4);
-        alloc((void**)&e->tp_flags, 256);
+        // receive buffers of the fused GEMM + all-reduce: one [Mx, hidden] fp32 slot per source rank (the separate
+        // all-reduce kernel only uses slot 0); flags: 64 words for that kernel + [kTpFlagSlots][8] for the fused path
+        const size_t flag_bytes = 256 + (size_t)kTpFlagSlots * 8 * 4;
+        alloc((void**)&e->tp_buf[0], (size_t)c.tp_size * Mx * c.hidden * 4);
+        alloc((void**)&e->tp_buf[1], (size_t)c.tp_size * Mx * c.hidden * 4);
+        alloc((void**)&e->tp_flags, flag_bytes);
         alloc((void**)&e->tp_error, 256);
         if (ok) {
-            cudaMemset(e->tp_flags, 0, 256);
+            cudaMemset(e->tp_flags, 0, flag_bytes);
             cudaMemset(e->tp_error, 0, 256);
         }
     }
@@ -525,6 +553,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "early_trigger")) g_gemm_early_trigger = value;
     else if (!strcmp(name, "headroom")) g_gemm_headroom = value;
     else if (!strcmp(name, "recv_dedicated")) g_gemm_recv_dedicated = value;
+    else if (!strcmp(name, "tp_fused")) e->tp_fused = value;
     else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;
     else if (!strcmp(name, "profile")) {
         e->profile = value;

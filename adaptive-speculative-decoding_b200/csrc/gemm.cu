@@ -53,6 +53,7 @@ struct GemmArgs {
     int l2_prefetch;    // k-blocks of weights (beyond the smem ring) each CTA pulls into L2 before the PDL wait
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
     NormFusion norm;
+    TpFusion tp;        // world > 1: all-reduce over peer memory inside the owner epilogue
     unsigned long long* trace;  // diagnostics: kTraceSlots globaltimer stamps per CTA (nullptr = off)
 };
 
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
         const int lgG = 29 - __clz(rows_per), G = 1 << lgG;            // log2(rows_per / 4)
         const int vq = et & (G - 1), vcstep = kTileN >> lgG;
         const int vn = tile_n * kTileN + (int)my_rank * rows_per + 4 * vq;
-        const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees ks >= 4 in this mode
+        const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees a power-of-two split >= 2 in this mode
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
         float lw[4] = {0.f, 0.f, 0.f, 0.f};
         // QKV owner: a thread keeps 4 consecutive rotary pairs of one head and walks the token rows
@@ -421,6 +422,57 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
             float* colsum = xbuf;                            // [MT] this owner's sum of squares per token
             const int items = a.MT << lgG;
             const bool n_ok = vn < a.n_valid;
+            const bool tpf = a.tp.world > 1;
+            auto cluster_sum = [&](int col) {                // the ks contributions of one float4, in rank order
+                float4 acc = recv4[(col << lgG) + vq];
+#pragma unroll
+                for (int src = 1; src < 8; ++src)
+                    if (src < ks) {
+                        const float4 t = recv4[((src * a.MT + col) << lgG) + vq];
+                        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+                    }
+                return acc;
+            };
+            if (tpf) {
+                // ---- tensor parallel, step 1: push this rank's partial into every rank's receive buffer
+                int col = et >> lgG;
+#pragma unroll 1
+                for (int g = et; g < items; g += 128, col += vcstep) {
+                    const int m = m0 + col;
+                    if (!(n_ok && m < a.M)) continue;
+                    const float4 acc = cluster_sum(col);
+                    const size_t off = (size_t)a.tp.rank * a.tp.slot_stride + (size_t)m * a.ldo + vn;
+                    for (int p = 0; p < a.tp.world; ++p)
+                        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.tp.recv[p] + off), "f"(acc.x),
+                                     "f"(acc.y), "f"(acc.z), "f"(acc.w)
+                                     : "memory");
+                }
+                if (threadIdx.x == 64) trace_stamp(a, 13);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // step 2: publish (release, system scope: cumulative over the stores ordered by the barrier) ...
+                const int slot = ((tile_m * gridDim.x + tile_n) * ks + (int)my_rank) * 8;
+                if (et < a.tp.world && et != a.tp.rank) {
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.tp.flags[et] + slot + a.tp.rank),
+                                 "r"(a.tp.epoch)
+                                 : "memory");
+                    // ... and wait for the same owner CTA of that peer (acquire, bounded spin)
+                    const uint32_t* f = a.tp.flags[a.tp.rank] + slot + et;
+                    uint32_t seen;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                        if ((int)(seen - a.tp.epoch) >= 0) break;
+                        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; fail loudly, do not hang
+                            *a.tp.error = 1;
+                            break;
+                        }
+                    } while (true);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 64) trace_stamp(a, 14);
+            }
+            const float* mine = tpf ? a.tp.recv[a.tp.rank] : nullptr;
             int col = et >> lgG;
 #pragma unroll 1
             for (int g = et; g < items; g += 128, col += vcstep) {
@@ -429,13 +481,17 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
                 float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (a.accumulate && n_ok && g + 128 < items && m + vcstep < a.M)
                     nxt = *reinterpret_cast<const float4*>(o + (size_t)vcstep * a.ldo);
-                float4 acc = recv4[(col << lgG) + vq];
-#pragma unroll
-                for (int src = 1; src < 8; ++src)
-                    if (src < ks) {
-                        const float4 t = recv4[((src * a.MT + col) << lgG) + vq];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!tpf) {
+                    acc = cluster_sum(col);
+                } else if (n_ok && m < a.M) {
+                    // step 3: the world partials of this float4, read from my own memory, added in rank order
+                    const float* src = mine + (size_t)m * a.ldo + vn;
+                    for (int r = 0; r < a.tp.world; ++r) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * a.tp.slot_stride));
                         acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
                     }
+                }
                 float sq = 0.0f;
                 if (n_ok && m < a.M) {
                     if (a.accumulate) acc.x = old.x + acc.x, acc.y = old.y + acc.y, acc.z = old.z + acc.z, acc.w = old.w + acc.w;
@@ -705,7 +761,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
 
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
                 int n_valid, bool pdl, cudaStream_t stream, bool accumulate, const QkvEpilogue* qkv,
-                const NormFusion* norm) {
+                const NormFusion* norm, const TpFusion* tp) {
     if (!g_gemm_attr_set) {
         if (device_props()) return -1;
         ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
@@ -733,6 +789,15 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.l2_prefetch = (pdl && g_gemm_prefetch_next) ? g_gemm_l2_prefetch : 0;
     g_gemm_prefetch_next = 0;
     a.norm = norm ? *norm : NormFusion{};
+    a.tp = TpFusion{};
+    if (tp && tp->world > 1) {
+        if (!pl.reduce || pl.mode != GEMM_OUT_F32 || (pl.ksplit != 2 && pl.ksplit != 4 && pl.ksplit != 8) ||
+            ((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
+            return set_error("gemm: the fused all-reduce needs the cluster reduction on 16-byte aligned rows");
+        if (pl.m_tiles * pl.n_tiles * pl.ksplit > kTpFlagSlots) return set_error("gemm: too many owner CTAs for the fused all-reduce");
+        if ((size_t)pl.M * ldo > tp->slot_stride) return set_error("gemm: receive slot smaller than the output");
+        a.tp = *tp;
+    }
     a.trace = nullptr;
     if (g_gemm_trace && g_gemm_trace_next < g_gemm_trace_max) {
         a.trace = g_gemm_trace + (size_t)g_gemm_trace_next * kTraceCtas * kTraceSlots;
@@ -740,8 +805,8 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
         ++g_gemm_trace_next;
     }
     if (a.norm.sumsq_out != nullptr) {
-        if (!pl.reduce || pl.ksplit < 4 || pl.mode != GEMM_OUT_F32)
-            return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction with ksplit >= 4");
+        if (!pl.reduce || pl.ksplit < 2 || pl.mode != GEMM_OUT_F32)
+            return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction (ksplit >= 2)");
         if (!a.norm.resid_bf || !a.norm.ln_w) return set_error("gemm: fused norm producer needs resid_bf and ln_w");
         if (((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || (pl.ksplit & (pl.ksplit - 1)))
             return set_error("gemm: fused norm producer needs 16-byte aligned rows and a power-of-two split");

@@ -22,6 +22,21 @@ struct NormFusion {
     const __nv_bfloat16* ln_w = nullptr; // producer: [N] weight of the NEXT RMSNorm
 };
 
+// Tensor-parallel row-parallel projection, fused: the owner CTAs of the in-cluster split-K reduction PUSH their
+// fp32 partial tile into every rank's receive buffer over NVLink peer memory (slot = source rank), publish a
+// per-(owner CTA, source rank) flag with system-scope release, wait for the same owner CTA of every peer, and
+// then add the `world` partials in rank order (bit-identical on all ranks) onto the residual - the all-reduce
+// happens inside the GEMM epilogue, tile by tile, with no separate collective launch.
+constexpr int kTpFlagSlots = 4096;       // owner CTAs per launch that can be tracked ([slot][8] u32 per rank)
+struct TpFusion {
+    float* recv[8] = {};       // this launch's receive buffer of every rank: [world][slot_stride] fp32 (peer-mapped)
+    uint32_t* flags[8] = {};   // fused-flag array of every rank: flags[p][slot * 8 + src] = last epoch src published
+    int rank = 0, world = 1;
+    uint32_t epoch = 0;
+    int* error = nullptr;      // set to 1 if a peer never showed up (bounded spin)
+    size_t slot_stride = 0;    // floats between the per-source slots of a receive buffer
+};
+
 // extra operands of the fused QKV epilogue (bias + rotate-half RoPE + q store + paged K/V append)
 struct QkvEpilogue {
     const float2* cs;               // [M, hd/2] (cos, sin) of each token's position
@@ -52,6 +67,6 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // GEMM_OUT_SWIGLU -> bf16 [M][ldo] with N/2 columns (n_valid = ff)
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
                 int n_valid, bool pdl, cudaStream_t stream, bool accumulate = false,
-                const QkvEpilogue* qkv = nullptr, const NormFusion* norm = nullptr);
+                const QkvEpilogue* qkv = nullptr, const NormFusion* norm = nullptr, const TpFusion* tp = nullptr);
 
 }  // namespace asd
