@@ -403,8 +403,12 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
         // receive buffers of the fused GEMM + all-reduce: one [Mx, hidden] fp32 slot per source rank (the separate
         // all-reduce kernel only uses slot 0); flags: 64 words for that kernel + [kTpFlagSlots][8] for the fused path
         const size_t flag_bytes = 256 + (size_t)kTpFlagSlots * 8 * 4;
-        alloc((void**)&e->tp_buf[0], (size_t)c.tp_size * Mx * c.hidden * 4);
-        alloc((void**)&e->tp_buf[1], (size_t)c.tp_size * Mx * c.hidden * 4);
+        alloc((void**)&e->tp_buf[0], (size_t)c.tp_size * Mx * c.hidden * 8);   // {value, epoch} word pairs
+        alloc((void**)&e->tp_buf[1], (size_t)c.tp_size * Mx * c.hidden * 8);
+        if (ok) {
+            cudaMemset(e->tp_buf[0], 0, (size_t)c.tp_size * Mx * c.hidden * 8);   // epoch 0 never matches a launch
+            cudaMemset(e->tp_buf[1], 0, (size_t)c.tp_size * Mx * c.hidden * 8);
+        }
         alloc((void**)&e->tp_flags, flag_bytes);
         alloc((void**)&e->tp_error, 256);
         if (ok) {

@@ -303,44 +303,43 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
     }
     if (a.reduce) {
         // ---- split-K reduction inside the cluster (deterministic, no HBM round trip of partials):
-        // CTA r of the cluster owns accumulator rows [r*rows_per, (r+1)*rows_per); every CTA sends
-        // those rows of its partial tile into the owner's (now idle) smem ring through DSMEM, the
-        // owner adds the ksplit contributions in rank order and writes the final values once.
-        // The owner loops below are kept rolled and 128-bit wide on purpose: every CTA runs them exactly
-        // once, so straight-line unrolled code is paid for in instruction-cache misses, not saved.
-        const int ks = a.ksplit, rows_per = (kTileN + ks - 1) / ks;
+        // CTA r of the cluster owns the token columns [r*cols_per, (r+1)*cols_per) of the tile; every CTA sends
+        // those columns of its partial accumulator (all 128 rows) into the owner's shared memory through DSMEM,
+        // the owner adds the ksplit contributions in rank order and runs the epilogue for its tokens.  Owning
+        // whole tokens keeps every run contiguous: a warp's DSMEM store is 128 bytes, an owner reads float4s and
+        // writes 512-byte rows, the per-token sum of squares and the rotary pairs of a head never leave the CTA.
+        // The owner loops are kept rolled and 128-bit wide on purpose: every CTA runs them exactly once, so
+        // straight-line unrolled code is paid for in instruction-cache misses, not saved.
+        const int ks = a.ksplit, cols_per = (a.MT + ks - 1) / ks;
         const uint32_t my_rank = cluster_ctarank();
         const bool qkv = a.mode == GEMM_OUT_QKV;
-        const int hd = qkv ? a.qkv.hd : kTileN, half = hd >> 1, pp = half / ks;
         const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads (warps 2..5)
         const int m0 = tile_m * a.MT;
+        const int c_first = (int)my_rank * cols_per;     // first tile column (token) this CTA owns
+        const int c_cnt = max(0, min(cols_per, a.MT - c_first));
         float* const outf = static_cast<float*>(a.out);
-        // fp32 owner, vector form: rows_per = 4 G, G a power of two; a thread keeps its 4 output columns
-        // n .. n+3 and walks the token rows 128 / G at a time
-        const bool vec = !qkv && (ks == 2 || ks == 4 || ks == 8) && ((a.ldo | a.n_valid) & 3) == 0 &&
-                         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
-        const int lgG = 29 - __clz(rows_per), G = 1 << lgG;            // log2(rows_per / 4)
-        const int vq = et & (G - 1), vcstep = kTileN >> lgG;
-        const int vn = tile_n * kTileN + (int)my_rank * rows_per + 4 * vq;
-        const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees a power-of-two split >= 2 in this mode
+        const bool vec = !qkv && ((a.ldo | a.n_valid) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+        const bool emit = a.norm.sumsq_out != nullptr;   // host guarantees vec in this mode
+        const bool tpf = a.tp.world > 1;                 // host guarantees vec in this mode
+        // fp32 owner: thread = (4 consecutive output columns n, token t = warp, warp + 4, ...)
+        const int n4 = et & 31, vn = tile_n * kTileN + 4 * n4;
+        const bool n_ok = vn < a.n_valid;
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
         float lw[4] = {0.f, 0.f, 0.f, 0.f};
-        // QKV owner: a thread keeps 4 consecutive rotary pairs of one head and walks the token rows
+        // QKV owner: thread = (4 consecutive rotary pairs of one head, token t = et / 16, + 8, ...)
+        const int hd = qkv ? a.qkv.hd : kTileN, half = hd >> 1;
         const int heads_per_tile = kTileN / hd;
-        const int lgP = qkv ? 31 - __clz(heads_per_tile * pp) - 2 : 0;  // log2(pair groups per token)
-        const int ppg = pp >> 2;                                        // pair groups per head
-        const int qh2 = (et & ((1 << lgP) - 1)) / (ppg > 0 ? ppg : 1);
-        const int qpq = ((et & ((1 << lgP) - 1)) - qh2 * ppg) * 4;
-        const int qhead = tile_n * heads_per_tile + qh2;                // q heads, then k heads, then v heads
-        const int qi = (int)my_rank * pp + qpq;                         // first dim index of the 4 pairs
-        int* const kvrow = reinterpret_cast<int*>(xbuf);                // [MT] cache row of each token (kv head 0)
+        const int gi = et & 15;
+        const int qh2 = hd == 64 ? gi >> 3 : 0, qi = hd == 64 ? (gi & 7) * 4 : gi * 4;   // head in tile, first pair
+        const int qhead = tile_n * heads_per_tile + qh2;                                // q heads, then k, then v
+        int* const kvrow = reinterpret_cast<int*>(xbuf);                // [cols_per] cache row of each owned token
         float qb1[4] = {0.f, 0.f, 0.f, 0.f}, qb2[4] = {0.f, 0.f, 0.f, 0.f};
         if (warp >= 2) {
             // operands that do not depend on this GEMM are fetched before the cluster barriers
             if (vec) {
-                const int m = m0 + (et >> lgG);
-                if (vn < a.n_valid) {
-                    if (a.accumulate && m < a.M && et < (a.MT << lgG))
+                const int t = et >> 5, m = m0 + c_first + t;
+                if (n_ok) {
+                    if (a.accumulate && t < c_cnt && m < a.M)
                         old = *reinterpret_cast<const float4*>(outf + (size_t)m * a.ldo + vn);
                     if (emit) {
                         const uint2 w4 = *reinterpret_cast<const uint2*>(a.norm.ln_w + vn);
@@ -361,15 +360,15 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
                     qb1[0] = a01.x, qb1[1] = a01.y, qb1[2] = a23.x, qb1[3] = a23.y;
                     qb2[0] = c01.x, qb2[1] = c01.y, qb2[2] = c23.x, qb2[3] = c23.y;
                 }
-                for (int c = et; c < a.MT; c += 128) {
-                    const int m = m0 + c;
+                for (int t = et; t < c_cnt; t += 128) {
+                    const int m = m0 + c_first + t;
                     int r = 0;
                     if (m < a.M) {
                         const int pos = e.positions[m];
                         const int page = e.page_table[(size_t)e.token_slot[m] * e.max_pages + pos / e.page_size];
                         r = page * e.nkv * e.page_size + pos % e.page_size;
                     }
-                    kvrow[c] = r;
+                    kvrow[t] = r;
                 }
             }
         }
@@ -377,39 +376,34 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
         tc_fence_after();
         uint8_t* recv_base = smem;               // the receive buffer overlays the (idle) tile ring ...
         if (a.recv_dedicated) {                  // ... or, for small token tiles, has its own shared memory
-            const int xb_floats = qkv ? a.MT : 256 + 8 * a.MT;
-            recv_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xbuf + xb_floats) + 15) & ~uintptr_t(15));
+            recv_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xbuf + (qkv ? a.MT : 0)) + 15) & ~uintptr_t(15));
             cluster_wait();
         } else {
             fence_proxy_async_smem();
             cluster_sync();                      // every CTA of the cluster is done with its ring
         }
         if (threadIdx.x == 64) trace_stamp(a, 5);
-        // receive layout in the owner: recv[src][col][lrow] (lrow contiguous) so that the 32 lanes of a
-        // warp (32 consecutive accumulator rows) write contiguous 64-128 byte runs through DSMEM
-        // QKV mode keeps the two halves of every rotary pair in the same owner: within a head, pair p
-        // (dims p and p + hd/2) goes to owner p / pp, pp = (hd/2) / ks pairs per owner per head.
+        // receive layout in the owner: recv[src][owned column][128 rows] - the 32 lanes of a warp (32 consecutive
+        // accumulator rows) write one contiguous 128-byte run per column
         if (warp >= 2) {
             const int q = warp & 3, row = q * 32 + lane;
-            int owner, lrow;
-            if (qkv) {
-                const int h2 = row / hd, within = row - h2 * hd, hi = within / half, pr = within - hi * half;
-                owner = pr / pp;
-                lrow = (h2 * 2 + hi) * pp + (pr - owner * pp);
-            } else {
-                owner = row / rows_per;
-                lrow = row - owner * rows_per;
-            }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-            const uint32_t dst = mapa(smem_u32(recv_base) + (uint32_t)((int)my_rank * a.MT * rows_per + lrow) * 4u,
-                                      (uint32_t)owner);
+            const uint32_t mine = smem_u32(recv_base) + (uint32_t)((int)my_rank * cols_per * kTileN + row) * 4u;
+            int owner = 0, lc = 0;               // owner CTA and local column of tile column c0 + i
             for (int c0 = 0; c0 < a.MT; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c0, r);
                 tmem_ld_wait();
+                uint32_t dst = mapa(mine, (uint32_t)owner);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < a.MT) st_cluster_u32(dst + (uint32_t)((c0 + i) * rows_per) * 4u, r[i]);
+                for (int i = 0; i < 32; ++i) {
+                    if (c0 + i < a.MT) st_cluster_u32(dst + (uint32_t)(lc * kTileN) * 4u, r[i]);
+                    if (++lc == cols_per) {
+                        lc = 0;
+                        ++owner;
+                        dst = mapa(mine, (uint32_t)(owner < ks ? owner : 0));
+                    }
+                }
             }
             tc_fence_before();
         }
@@ -419,77 +413,83 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
         const float* recv = reinterpret_cast<const float*>(recv_base);
         const float4* recv4 = reinterpret_cast<const float4*>(recv_base);
         if (warp >= 2 && vec) {
-            float* colsum = xbuf;                            // [MT] this owner's sum of squares per token
-            const int items = a.MT << lgG;
-            const bool n_ok = vn < a.n_valid;
-            const bool tpf = a.tp.world > 1;
-            auto cluster_sum = [&](int col) {                // the ks contributions of one float4, in rank order
-                float4 acc = recv4[(col << lgG) + vq];
+            auto cluster_sum = [&](int t) {                  // the ks contributions of one float4, in rank order
+                float4 acc = recv4[(t << 5) + n4];
 #pragma unroll
                 for (int src = 1; src < 8; ++src)
                     if (src < ks) {
-                        const float4 t = recv4[((src * a.MT + col) << lgG) + vq];
-                        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+                        const float4 v = recv4[((src * cols_per + t) << 5) + n4];
+                        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
                     }
                 return acc;
             };
             if (tpf) {
-                // ---- tensor parallel, step 1: push this rank's partial into every rank's receive buffer
-                int col = et >> lgG;
+                // ---- tensor parallel, step 1: push this rank's partial rows into every peer's receive buffer.
+                // Flags travel WITH the data (every 8-byte word = {value, epoch}, 16-byte stores), so there is no
+                // system-scope fence and no separate flag round trip: a fence behind 2 MB of NVLink stores costs
+                // 8-10 us (measured), the inline flag costs the one-way latency.
+                const uint32_t ep = a.tp.epoch;
 #pragma unroll 1
-                for (int g = et; g < items; g += 128, col += vcstep) {
-                    const int m = m0 + col;
+                for (int t = et >> 5; t < c_cnt; t += 4) {
+                    const int m = m0 + c_first + t;
                     if (!(n_ok && m < a.M)) continue;
-                    const float4 acc = cluster_sum(col);
-                    const size_t off = (size_t)a.tp.rank * a.tp.slot_stride + (size_t)m * a.ldo + vn;
-                    for (int p = 0; p < a.tp.world; ++p)
-                        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.tp.recv[p] + off), "f"(acc.x),
-                                     "f"(acc.y), "f"(acc.z), "f"(acc.w)
+                    const float4 acc = cluster_sum(t);
+                    const size_t off = 2 * ((size_t)a.tp.rank * a.tp.slot_stride + (size_t)m * a.ldo + vn);
+                    for (int p = 0; p < a.tp.world; ++p) {
+                        if (p == a.tp.rank) continue;
+                        float* d = a.tp.recv[p] + off;
+                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(d), "r"(__float_as_uint(acc.x)),
+                                     "r"(ep), "r"(__float_as_uint(acc.y))
                                      : "memory");
+                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(d + 4), "r"(__float_as_uint(acc.z)),
+                                     "r"(ep), "r"(__float_as_uint(acc.w))
+                                     : "memory");
+                    }
                 }
                 if (threadIdx.x == 64) trace_stamp(a, 13);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                // step 2: publish (release, system scope: cumulative over the stores ordered by the barrier) ...
-                const int slot = ((tile_m * gridDim.x + tile_n) * ks + (int)my_rank) * 8;
-                if (et < a.tp.world && et != a.tp.rank) {
-                    __threadfence_system();
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.tp.flags[et] + slot + a.tp.rank),
-                                 "r"(a.tp.epoch)
-                                 : "memory");
-                    // ... and wait for the same owner CTA of that peer (acquire, bounded spin)
-                    const uint32_t* f = a.tp.flags[a.tp.rank] + slot + et;
-                    uint32_t seen;
-                    const long long t0 = clock64();
-                    do {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-                        if ((int)(seen - a.tp.epoch) >= 0) break;
-                        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; fail loudly, do not hang
-                            *a.tp.error = 1;
-                            break;
-                        }
-                    } while (true);
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (threadIdx.x == 64) trace_stamp(a, 14);
             }
             const float* mine = tpf ? a.tp.recv[a.tp.rank] : nullptr;
-            int col = et >> lgG;
 #pragma unroll 1
-            for (int g = et; g < items; g += 128, col += vcstep) {
-                const int m = m0 + col;
+            for (int t = et >> 5; t < c_cnt; t += 4) {       // t is warp-uniform
+                const int m = m0 + c_first + t;
                 float* o = outf + (size_t)m * a.ldo + vn;
                 float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.accumulate && n_ok && g + 128 < items && m + vcstep < a.M)
-                    nxt = *reinterpret_cast<const float4*>(o + (size_t)vcstep * a.ldo);
+                if (a.accumulate && n_ok && t + 4 < c_cnt && m + 4 < a.M)
+                    nxt = *reinterpret_cast<const float4*>(o + (size_t)4 * a.ldo);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (!tpf) {
-                    acc = cluster_sum(col);
+                    acc = cluster_sum(t);
                 } else if (n_ok && m < a.M) {
-                    // step 3: the world partials of this float4, read from my own memory, added in rank order
-                    const float* src = mine + (size_t)m * a.ldo + vn;
+                    // step 2: the world partials of this float4 in rank order (bit-identical on every rank): my own
+                    // from the cluster, the peers' from my receive buffer as soon as their inline flags show up
+                    const uint32_t ep = a.tp.epoch;
                     for (int r = 0; r < a.tp.world; ++r) {
-                        const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * a.tp.slot_stride));
-                        acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+                        float4 v;
+                        if (r == a.tp.rank) {
+                            v = cluster_sum(t);
+                        } else {
+                            const float* src = mine + 2 * ((size_t)r * a.tp.slot_stride + (size_t)m * a.ldo + vn);
+                            uint4 w0, w1;
+                            const long long t0 = clock64();
+                            do {
+                                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w)
+                                             : "l"(src)
+                                             : "memory");
+                                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w)
+                                             : "l"(src + 4)
+                                             : "memory");
+                                if (w0.y == ep && w0.w == ep && w1.y == ep && w1.w == ep) break;
+                                if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; fail loudly, do not hang
+                                    *a.tp.error = 1;
+                                    break;
+                                }
+                            } while (true);
+                            v = make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x),
+                                            __uint_as_float(w1.z));
+                        }
+                        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
                     }
                 }
                 float sq = 0.0f;
@@ -506,59 +506,40 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
                         sq = (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
                     }
                 }
-                if (emit) {   // the G lanes that share this token are consecutive: tree-reduce them
-                    for (int d = G >> 1; d >= 1; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-                    if (vq == 0) colsum[col] = sq;
+                if (emit) {   // the whole warp works on token m: its sum is this tile's share of the norm statistics
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+                    if (lane == 0 && m < a.M) a.norm.sumsq_out[(size_t)tile_n * a.norm.ld + m] = sq;
                 }
                 old = nxt;
             }
         } else if (warp >= 2 && !qkv) {
-            // generic owner (any split, unaligned output): one element per thread and step
-            const int first = (int)my_rank * rows_per;
-            const int nrows = min(rows_per, kTileN - first);
+            // generic owner (unaligned output): one element per thread and step
 #pragma unroll 1
-            for (int idx = et; idx < rows_per * a.MT; idx += 128) {
-                const int col = idx / rows_per, lrow = idx - col * rows_per;
+            for (int idx = et; idx < c_cnt * kTileN; idx += 128) {
+                const int t = idx >> 7, rw = idx & (kTileN - 1);
                 float acc = recv[idx];
 #pragma unroll 1
-                for (int src = 1; src < ks; ++src) acc += recv[src * a.MT * rows_per + idx];
-                const int n = tile_n * kTileN + first + lrow, m = m0 + col;
-                if (lrow < nrows && m < a.M && n < a.n_valid) {
+                for (int src = 1; src < ks; ++src) acc += recv[src * cols_per * kTileN + idx];
+                const int n = tile_n * kTileN + rw, m = m0 + c_first + t;
+                if (m < a.M && n < a.n_valid) {
                     float* o = outf + (size_t)m * a.ldo + n;
                     *o = a.accumulate ? *o + acc : acc;
                 }
             }
         }
         if (threadIdx.x == 64) trace_stamp(a, 10);
-        if (emit && !qkv) {
-            if (!vec) __trap();   // the host only asks for the norm producer on vectorisable shapes
-            if (warp >= 2) {
-                // owners -> rank 0 (DSMEM), rank 0 adds the ks values in rank order and publishes the tile's row
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const uint32_t g0 = mapa(smem_u32(xbuf + 256 + (int)my_rank * a.MT), 0);
-                for (int c = et; c < a.MT; c += 128) st_cluster_f32(g0 + c * 4, xbuf[c]);
-            }
-            cluster_sync();
-            if (warp >= 2 && my_rank == 0) {
-                for (int c = et; c < a.MT; c += 128) {
-                    float t = 0.0f;
-                    for (int r2 = 0; r2 < ks; ++r2) t += xbuf[256 + r2 * a.MT + c];
-                    if (m0 + c < a.M) a.norm.sumsq_out[(size_t)tile_n * a.norm.ld + m0 + c] = t;
-                }
-            }
-        }
+        if ((emit || tpf) && !qkv && !vec) __trap();   // the host only asks for these on vectorisable shapes
         if (qkv && warp >= 2) {
             // bias + RoPE + q store / paged K,V append: 4 rotary pairs (dims i..i+3 and i+half..) per thread and step
             const QkvEpilogue& e = a.qkv;
-            const int items = a.MT << lgP, cstep = kTileN >> lgP;
             const bool head_ok = qhead < e.nh + 2 * e.nkv;
             const bool rot = qhead < e.nh + e.nkv;
-            const int l1 = (qh2 * 2) * pp + qpq, l2 = (qh2 * 2 + 1) * pp + qpq;   // multiples of 4
+            const int f1 = (qh2 * hd + qi) >> 2, f2 = (qh2 * hd + half + qi) >> 2;   // float4 index inside a column
             const bool scale = a.norm.sumsq_in != nullptr;
-            int col = et >> lgP;
 #pragma unroll 1
-            for (int g = et; g < items; g += 128, col += cstep) {
-                const int m = m0 + col;
+            for (int t = et >> 4; t < c_cnt; t += 8) {
+                const int m = m0 + c_first + t;
                 if (m >= a.M || !head_ok) continue;
                 float4 c01 = make_float4(1.f, 0.f, 1.f, 0.f), c23 = c01;          // (cos, sin) pairs
                 if (rot) {
@@ -566,17 +547,17 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
                     c01 = cs4[0];
                     c23 = cs4[1];
                 }
-                float4 x1 = recv4[(col * rows_per + l1) >> 2], x2 = recv4[(col * rows_per + l2) >> 2];
+                float4 x1 = recv4[(t << 5) + f1], x2 = recv4[(t << 5) + f2];
 #pragma unroll
                 for (int src = 1; src < 8; ++src)
                     if (src < ks) {
-                        const float4 t1 = recv4[((src * a.MT + col) * rows_per + l1) >> 2];
-                        const float4 t2 = recv4[((src * a.MT + col) * rows_per + l2) >> 2];
+                        const float4 t1 = recv4[((src * cols_per + t) << 5) + f1];
+                        const float4 t2 = recv4[((src * cols_per + t) << 5) + f2];
                         x1.x += t1.x, x1.y += t1.y, x1.z += t1.z, x1.w += t1.w;
                         x2.x += t2.x, x2.y += t2.y, x2.z += t2.z, x2.w += t2.w;
                     }
                 if (scale) {
-                    const float rs = rstd_s[col];
+                    const float rs = rstd_s[c_first + t];
                     x1.x *= rs, x1.y *= rs, x1.z *= rs, x1.w *= rs;
                     x2.x *= rs, x2.y *= rs, x2.z *= rs, x2.w *= rs;
                 }
@@ -593,7 +574,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
                 } else {
                     const int kvh = rot ? qhead - e.nh : qhead - e.nh - e.nkv;
                     __nv_bfloat16* cache = rot ? e.k_cache : e.v_cache;
-                    dstp = cache + (size_t)(kvrow[col] + kvh * e.page_size) * hd;
+                    dstp = cache + (size_t)(kvrow[t] + kvh * e.page_size) * hd;
                 }
                 uint2 lo, hi;
                 lo.x = *reinterpret_cast<const uint32_t*>(&lo01);
@@ -693,7 +674,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     pl->kblocks = (K + kBlockK - 1) / kBlockK;
     const int stage_bytes = kABytes + pl->MT * 128;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + pl->MT * 4 /*rstd*/ +
-                      (mode == GEMM_OUT_F32 ? (256 + 8 * pl->MT) * 4 : (mode == GEMM_OUT_QKV ? pl->MT * 4 : 0));
+                      (mode == GEMM_OUT_QKV ? pl->MT * 4 : 0);   // QKV: cache row of each owned token
     const int max_ctas_per_sm = pl->MT <= 128 ? 3 : 2;   // TMEM: 128 / 256 columns per CTA
     const int tiles = pl->n_tiles * pl->m_tiles;
     // Split choice.  Measured on B200: one SM cannot ingest more than ~40 GB/s from HBM however deep its
@@ -733,8 +714,8 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     int recv_extra = 0;
     if (pl->reduce && (ksplit > 1 || mode == GEMM_OUT_QKV)) {
         if (ksplit > 8) return set_error("gemm: cluster reduction supports ksplit <= 8");
-        const int rows_per = (kTileN + ksplit - 1) / ksplit;
-        const int recv = ksplit * rows_per * pl->MT * 4;
+        const int cols_per = (pl->MT + ksplit - 1) / ksplit;
+        const int recv = ksplit * cols_per * kTileN * 4;
         if (pl->MT <= 32 && g_gemm_recv_dedicated) {
             pl->recv_dedicated = 1;                     // small tiles: own receive buffer, one cluster barrier less
             recv_extra = recv + 16;
@@ -791,8 +772,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.norm = norm ? *norm : NormFusion{};
     a.tp = TpFusion{};
     if (tp && tp->world > 1) {
-        if (!pl.reduce || pl.mode != GEMM_OUT_F32 || (pl.ksplit != 2 && pl.ksplit != 4 && pl.ksplit != 8) ||
-            ((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
+        if (!pl.reduce || pl.mode != GEMM_OUT_F32 || ((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
             return set_error("gemm: the fused all-reduce needs the cluster reduction on 16-byte aligned rows");
         if (pl.m_tiles * pl.n_tiles * pl.ksplit > kTpFlagSlots) return set_error("gemm: too many owner CTAs for the fused all-reduce");
         if ((size_t)pl.M * ldo > tp->slot_stride) return set_error("gemm: receive slot smaller than the output");
@@ -805,18 +785,17 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
         ++g_gemm_trace_next;
     }
     if (a.norm.sumsq_out != nullptr) {
-        if (!pl.reduce || pl.ksplit < 2 || pl.mode != GEMM_OUT_F32)
-            return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction (ksplit >= 2)");
+        if (!pl.reduce || pl.mode != GEMM_OUT_F32)
+            return set_error("gemm: the sum-of-squares epilogue needs the cluster reduction");
         if (!a.norm.resid_bf || !a.norm.ln_w) return set_error("gemm: fused norm producer needs resid_bf and ln_w");
-        if (((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || (pl.ksplit & (pl.ksplit - 1)))
-            return set_error("gemm: fused norm producer needs 16-byte aligned rows and a power-of-two split");
+        if (((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
+            return set_error("gemm: fused norm producer needs 16-byte aligned rows");
     }
     a.qkv = QkvEpilogue{};
     if (pl.mode == GEMM_OUT_QKV) {
         if (!qkv) return set_error("gemm: QKV epilogue needs its operands");
         a.qkv = *qkv;
-        const int half = qkv->hd / 2;
-        if ((qkv->hd != 64 && qkv->hd != 128) || half % pl.ksplit) return set_error("gemm: QKV epilogue shape");
+        if (qkv->hd != 64 && qkv->hd != 128) return set_error("gemm: QKV epilogue shape");
     }
     if (accumulate && pl.mode != GEMM_OUT_F32) return set_error("gemm: accumulate needs the fp32 epilogue");
     if (accumulate && pl.ksplit > 1 && !pl.reduce) return set_error("gemm: accumulate needs the cluster reduction");

@@ -23,14 +23,16 @@ struct NormFusion {
 };
 
 // Tensor-parallel row-parallel projection, fused: the owner CTAs of the in-cluster split-K reduction PUSH their
-// fp32 partial tile into every rank's receive buffer over NVLink peer memory (slot = source rank), publish a
-// per-(owner CTA, source rank) flag with system-scope release, wait for the same owner CTA of every peer, and
-// then add the `world` partials in rank order (bit-identical on all ranks) onto the residual - the all-reduce
-// happens inside the GEMM epilogue, tile by tile, with no separate collective launch.
-constexpr int kTpFlagSlots = 4096;       // owner CTAs per launch that can be tracked ([slot][8] u32 per rank)
+// fp32 partial rows into every peer's receive buffer over NVLink peer memory (slot = source rank) as
+// {value, epoch} word pairs - the flag travels with the data, so there is no system-scope fence and no flag round
+// trip - and then add the `world` partials in rank order (bit-identical on all ranks) onto the residual as soon as
+// the peers' words carry this launch's epoch.  The all-reduce happens inside the GEMM epilogue, row by row, with no
+// separate collective launch.  Receive buffers alternate with the epoch parity: a peer can only be one fused GEMM
+// ahead (it needs my push of launch e+1 to finish it), so launch e+2 never overwrites rows I still read.
+constexpr int kTpFlagSlots = 4096;       // (flag words of the separate all-reduce kernel's successor; kept for layout)
 struct TpFusion {
-    float* recv[8] = {};       // this launch's receive buffer of every rank: [world][slot_stride] fp32 (peer-mapped)
-    uint32_t* flags[8] = {};   // fused-flag array of every rank: flags[p][slot * 8 + src] = last epoch src published
+    float* recv[8] = {};       // this launch's receive buffer of every rank: [world][2 * slot_stride] words (peer-mapped)
+    uint32_t* flags[8] = {};   // unused by the inline-flag protocol
     int rank = 0, world = 1;
     uint32_t epoch = 0;
     int* error = nullptr;      // set to 1 if a peer never showed up (bounded spin)

@@ -45,22 +45,27 @@ ev[1].record()
 torch.cuda.synchronize()
 L.asd_debug_gemm_trace(None, 0)
 dist.barrier()
-if rank == 0:
+for rr in range(world):
+    dist.barrier()
+    if rank != rr:
+        continue
+    print("---- rank", rank)
     tr = buf.cpu().numpy().reshape(MAXL, stride // 16, 16)
     used = [i for i in range(MAXL) if tr[i, 0, 0] != 0]
     print("forward ms", ev[0].elapsed_time(ev[1]), "launches", len(used))
     base = used[30 * 4]
     T0 = None
-    for j in range(9):
+    for j in range(5):
         x = tr[base + j]
         x = x[x[:, 0] != 0].astype(np.int64)
         if T0 is None:
             T0 = x[:, 0].min()
         out = [f"ctas {len(x):4d}"]
         for c, nm in ((0, "entry"), (2, "upstream"), (3, "tile0"), (4, "mainloop"), (5, "bar1"), (7, "bar2"), (13, "pushed"),
-                      (14, "arrived"), (10, "owner"), (8, "exit")):
+                      (15, "flagged"), (14, "arrived"), (10, "owner"), (8, "exit")):
             v = x[:, c][x[:, c] > 0]
             out.append(f"{nm} " + ("-" if len(v) == 0 else f"{np.median(v - T0) / 1e3:6.1f}/{(v - T0).max() / 1e3:6.1f}"))
-        print(" ".join(out))
+        print(" ".join(out), flush=True)
+dist.barrier()
 comm.destroy()
 dist.destroy_process_group()
