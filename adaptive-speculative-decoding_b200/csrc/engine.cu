@@ -190,7 +190,13 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         const bool emit = fn && fuse && pl.reduce && pow2;
         const bool p2p_ok = tp && e->p2p && (pl.reduce || pl.ksplit == 1);
         if (p2p_ok) ++e->tp_epoch;
-        if (p2p_ok && e->tp_fused && fn && pl.reduce && pow2 && pl.m_tiles * pl.n_tiles * pl.ksplit <= kTpFlagSlots) {
+        // The fused exchange is a one-shot all-reduce whose words carry their own flag (2 x the bytes): measured on
+        // B200 it beats the separate all-reduce kernel while (world - 1) * M * hidden * 8 bytes stays small (TP2:
+        // verify 11.6 -> 10.3 ms); at TP4 and 96 tokens the 12 MB per GEMM saturate the links (12.4 vs 9.8 ms), so
+        // larger exchanges keep the pull-based kernel.  tp_fused = 2 forces the fused path.
+        const size_t push_bytes = (size_t)(c.tp_size - 1) * M * h * 8;
+        const bool fused_pays = e->tp_fused == 2 || c.tp_size == 2 || push_bytes <= (size_t)5 << 20;
+        if (p2p_ok && e->tp_fused && fused_pays && fn && pl.reduce && pow2) {
             // tensor parallel, fused: the GEMM's owner CTAs exchange their partial tiles over NVLink peer memory
             // and finish residual + norm statistics themselves - same five launches per layer as on one GPU
             PROF(PROF_GEMM);
