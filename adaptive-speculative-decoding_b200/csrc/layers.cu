@@ -16,8 +16,8 @@
 
 namespace asd {
 
-int g_glue_pdl = 1;
-static void glue_carveout();   // same shared-memory carve-out for every glue kernel (see prefer_max_smem)   // launch the glue kernels programmatically (they wait on griddepcontrol)
+int g_glue_pdl = 1;   // launch the glue kernels programmatically (they wait on griddepcontrol)
+static void glue_carveout();   // same shared-memory carve-out for every glue kernel (see prefer_max_smem)
 
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxVec = 8;  // float4 per thread -> hidden <= 8192
@@ -146,6 +146,11 @@ struct TpPeers {
     int rank, world;
     uint32_t epoch;
     int* error;            // set to 1 if a peer never showed up
+    // two-shot (world >= 4): row m is reduced by its home rank m % world only, which publishes the final row in
+    // its broadcast buffer; the other ranks fetch that row instead of all `world` partials
+    int two_shot;
+    const float* bcast[8]; // broadcast buffer of every rank (peer-mapped), [M][h] fp32
+    uint32_t* rowflags[8]; // rowflags[p][m] = last epoch whose final row m is readable in its home's buffer
 };
 
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
@@ -186,21 +191,60 @@ __global__ void __launch_bounds__(kNormThreads) tp_allreduce_norm_kernel(
     float4 v[kNormMaxVec];
     float ss = 0.0f;
     float4* rrow = reinterpret_cast<float4*>(resid + (size_t)m * h);
+    const int home = tp.two_shot ? m % tp.world : tp.rank;
+    if (home == tp.rank) {
+        float4* brow = tp.two_shot ? reinterpret_cast<float4*>(const_cast<float*>(tp.bcast[tp.rank]) + (size_t)m * h) : nullptr;
 #pragma unroll
-    for (int i = 0; i < kNormMaxVec; ++i) {
-        const int c = threadIdx.x + i * kNormThreads;
-        if (c < nvec) {
-            float4 x = rrow[c];
-            for (int r = 0; r < tp.world; ++r) {
-                const float4 p = ld_peer_f4(tp.buf[r] + (size_t)m * h + 4 * c);
-                x.x += p.x;
-                x.y += p.y;
-                x.z += p.z;
-                x.w += p.w;
+        for (int i = 0; i < kNormMaxVec; ++i) {
+            const int c = threadIdx.x + i * kNormThreads;
+            if (c < nvec) {
+                float4 x = rrow[c];
+                for (int r = 0; r < tp.world; ++r) {
+                    const float4 p = ld_peer_f4(tp.buf[r] + (size_t)m * h + 4 * c);
+                    x.x += p.x;
+                    x.y += p.y;
+                    x.z += p.z;
+                    x.w += p.w;
+                }
+                rrow[c] = x;
+                if (brow) brow[c] = x;
+                v[i] = x;
+                ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
             }
-            rrow[c] = x;
-            v[i] = x;
-            ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+        if (tp.two_shot) {
+            __syncthreads();   // the whole final row is written
+            if (threadIdx.x < tp.world && (int)threadIdx.x != tp.rank) {
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tp.rowflags[threadIdx.x] + m), "r"(tp.epoch)
+                             : "memory");
+            }
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            const uint32_t* f = tp.rowflags[tp.rank] + m;
+            uint32_t seen;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                if ((int)(seen - tp.epoch) >= 0) break;
+                if (clock64() - t0 > 4000000000LL) {
+                    *tp.error = 1;
+                    break;
+                }
+            } while (true);
+        }
+        __syncthreads();
+        const float* brow = tp.bcast[home] + (size_t)m * h;
+#pragma unroll
+        for (int i = 0; i < kNormMaxVec; ++i) {
+            const int c = threadIdx.x + i * kNormThreads;
+            if (c < nvec) {
+                const float4 x = ld_peer_f4(brow + 4 * c);   // residual + all partials, summed by the home rank
+                rrow[c] = x;
+                v[i] = x;
+                ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+            }
         }
     }
     const float tot = block_sum(ss, scratch);
@@ -228,7 +272,8 @@ __global__ void __launch_bounds__(kNormThreads) tp_allreduce_norm_kernel(
 
 int launch_tp_allreduce_norm(const float* const* peer_bufs, uint32_t* const* peer_flags, int rank, int world,
                              uint32_t epoch, int* error, float* resid, const __nv_bfloat16* w, __nv_bfloat16* xnorm,
-                             int M, int h, float eps, __nv_bfloat16* resid_bf, float* sumsq0, cudaStream_t stream) {
+                             int M, int h, float eps, __nv_bfloat16* resid_bf, float* sumsq0, cudaStream_t stream,
+                             const float* const* peer_bcast, uint32_t* const* peer_rowflags) {
     if (world > 8) return set_error("tp all-reduce: world size <= 8");
     if (h % 4 || h > kNormThreads * kNormMaxVec * 4) return set_error("tp all-reduce: hidden must be %%4 and <= 8192");
     TpPeers tp;
@@ -240,6 +285,11 @@ int launch_tp_allreduce_norm(const float* const* peer_bufs, uint32_t* const* pee
     tp.world = world;
     tp.epoch = epoch;
     tp.error = error;
+    tp.two_shot = peer_bcast != nullptr;
+    for (int r = 0; r < 8; ++r) {
+        tp.bcast[r] = (peer_bcast && r < world) ? peer_bcast[r] : nullptr;
+        tp.rowflags[r] = (peer_rowflags && r < world) ? peer_rowflags[r] : nullptr;
+    }
     glue_carveout();
     tp_allreduce_norm_kernel<<<M, kNormThreads, 0, stream>>>(tp, resid, w, xnorm, h, eps, resid_bf, sumsq0);
     ASD_CUDA(cudaGetLastError());

@@ -1,6 +1,7 @@
-"""Tensor-parallel engine on 2 GPUs (skipped on a single-GPU box): both TP boundaries - the fused
-peer-memory all-reduce kernel and the NCCL path - must reproduce the oracle's logits, and all ranks must
-produce bit-identical logits (they stay in lock step without exchanging tokens)."""
+"""Tensor-parallel engine on 2 GPUs (skipped on a single-GPU box): every TP boundary - the all-reduce fused
+into the GEMM epilogue (inline-flag pushes over peer memory), the one-shot and two-shot peer-memory
+all-reduce kernels and the NCCL path - must reproduce the oracle's logits, and all ranks must produce
+bit-identical logits (they stay in lock step without exchanging tokens)."""
 import os
 import socket
 
@@ -18,7 +19,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, p2p, out):
+def _worker(rank, world, port, mode, out):
+    p2p = mode != "nccl"
     import torch.distributed as dist
     from asd_b200.engine import QwenEngine
     from asd_b200.models.qwen2 import Qwen2Config, random_hf_weights
@@ -36,6 +38,9 @@ def _worker(rank, world, port, p2p, out):
     eng.set_allreduce(comm.comm_ptr, comm.allreduce_fn_ptr)
     if p2p:
         eng.enable_p2p()
+    if mode in ("kernel", "two_shot"):
+        eng.set_option("tp_fused", 0)
+        eng.set_option("tp_two_shot", 1 if mode == "two_shot" else 0)
     slots = torch.arange(3, dtype=torch.int32, device=dev)
     idc = ids.to(dev).to(torch.int32)
     eng.prefill(idc[:, :64], slots)
@@ -57,10 +62,10 @@ def _worker(rank, world, port, p2p, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("p2p", [True, False])
-def test_tp2_logits_match_oracle(p2p):
+@pytest.mark.parametrize("mode", ["fused", "kernel", "two_shot", "nccl"])
+def test_tp2_logits_match_oracle(mode):
     import torch.multiprocessing as mp
     out = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), p2p, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
     assert out["err"] <= 2e-2 and out["agree"] >= 0.99, dict(out)
     assert out["identical"] and out["tp_error"] == 0, dict(out)
