@@ -247,7 +247,11 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             // rank moves 2 (W-1)/W payloads instead of W-1 (TP8, 96 tokens: 3.4 MB instead of 13.8 MB per boundary).
             // Measured on 8 B200: 12.4 ms per verify forward against 11.1 ms one-shot - at these sizes the exchange is
             // bound by the second flag hop (fence.sys + release), not by bytes - so one-shot stays the default.
-            const bool two = e->tp_two_shot == 1;
+            // It pays once bytes dominate: saved traffic (W-1 - 2 (W-1)/W) * M * hidden * 4 >= 16 MB per boundary
+            // (72B, 576 tokens, TP4: 56 -> 28 MB per boundary).  tp_two_shot = 1 forces it, -1 disables it.
+            const double payload = (double)M * h * 4.0, w1 = c.tp_size - 1;
+            const bool two = e->tp_two_shot == 1 ||
+                             (e->tp_two_shot == 0 && (w1 - 2.0 * w1 / c.tp_size) * payload >= 16.0 * (1 << 20));
             const float* bc[8] = {};
             uint32_t* rf[8] = {};
             for (int r = 0; r < c.tp_size; ++r) {

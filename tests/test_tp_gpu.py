@@ -40,7 +40,7 @@ def _worker(rank, world, port, mode, out):
         eng.enable_p2p()
     if mode in ("kernel", "two_shot"):
         eng.set_option("tp_fused", 0)
-        eng.set_option("tp_two_shot", 1 if mode == "two_shot" else 0)
+        eng.set_option("tp_two_shot", 1 if mode == "two_shot" else -1)
     slots = torch.arange(3, dtype=torch.int32, device=dev)
     idc = ids.to(dev).to(torch.int32)
     eng.prefill(idc[:, :64], slots)
