@@ -260,8 +260,8 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
                          # dram__bytes_read + dram__bytes_write of the four GEMM launches of one 32B layer, ncu --set
-                         # full (profiles/ncu_gemm_verify_r01_v3.txt): 1001.5 MB vs 975.2 MB algorithmic = 1.027 x
-                         "traffic": (layer_bytes + head_bytes) * 1.027 if (world == 1 and args.workload == "32b") else None,
+                         # full (profiles/ncu_gemm_verify_r01_v4.txt): 998.3 MB vs 975.2 MB algorithmic = 1.024 x
+                         "traffic": (layer_bytes + head_bytes) * 1.024 if (world == 1 and args.workload == "32b") else None,
                          "bytes_per_forward": layer_bytes + head_bytes, "ms_per_forward": roof_ms},
             "verify_step_us": verify_ms_timed * 1e3, "draft_step_us": draft_ms * 1e3,
             "verify_step_hbm_frac": (tcfg.streamed_bytes() / world + kv_bytes) / (verify_ms_timed * 1e-3) / 1e9 / peak,
