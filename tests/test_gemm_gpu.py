@@ -76,3 +76,29 @@ def test_linear_swiglu(M, ff, K):
     ref = torch.nn.functional.silu(gr) * ur
     scale = ref.abs().max().item()
     assert (y.float() - ref).abs().max().item() <= 8e-3 * scale
+
+
+def test_gemm_trace_stamps_are_ordered():
+    """asd_debug_gemm_trace: every CTA of a traced launch records increasing globaltimer stamps
+    (entry <= setup <= first tile <= main loop <= exit) and its SM id; tracing switches off again."""
+    import torch
+    from asd_b200 import _lib
+    from asd_b200.ops import linear_bf16
+    L = _lib.lib()
+    stride = L.asd_debug_gemm_trace(None, 0)
+    assert stride % 16 == 0
+    buf = torch.zeros(2 * stride, dtype=torch.int64, device="cuda")
+    x = torch.randn(96, 1024, device="cuda").bfloat16()
+    w = (torch.randn(512, 1024, device="cuda") * 0.05).bfloat16()
+    L.asd_debug_gemm_trace(buf.data_ptr(), 2)
+    y = linear_bf16(x, w, 3, 4, 0)
+    torch.cuda.synchronize()
+    L.asd_debug_gemm_trace(None, 0)
+    y2 = linear_bf16(x, w, 3, 4, 0)          # untraced launch gives the same result
+    assert torch.equal(y, y2)
+    tr = buf.cpu().view(2, stride // 16, 16)[0]
+    live = tr[tr[:, 0] != 0]
+    assert live.shape[0] == 4 * 4             # 4 weight tiles x 4 K splits
+    for c0, c1 in ((0, 1), (1, 3), (3, 4), (4, 8)):
+        assert bool((live[:, c0] <= live[:, c1]).all()), (c0, c1)
+    assert int(live[:, 9].max()) < 148 + 16

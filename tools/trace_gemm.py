@@ -1,4 +1,7 @@
 """Per-CTA timeline of every weight-streaming GEMM of one draft-then-verify step (asd_debug_gemm_trace).
+Stamps: entry, setup (barriers + TMEM), upstream (PDL wait returned), tile0 (first k-block landed), mainloop (last
+MMA committed), bar1 / scatter / bar2 (cluster split-K reduction; for the SwiGLU GEMM: transposed / - / -), owner
+(owner loop done), exit.  A layer launches QKV (56 tiles x 4 splits = 224 CTAs for 32B), O (320), gate|up (432), down (320).
 
 Prints, for each distinct GEMM of the verify forward (by position inside a layer), the median over the
 middle layers of: launch-to-launch period, kernel span, and the phase stamps relative to the first CTA's
@@ -53,9 +56,9 @@ for i in used:
     x = x[:n]
     info.append(dict(i=i, n=n, t0=x[:, 0].min(), t1=x[:, 8].max(), x=x))
 # the verify forward is the tail: 64 layers x 4 GEMMs + lm_head
-ver = info[-(64 * 4 + 2):]   # (slot 0 of a layer group = the previous layer's down projection)
-names = ["down(l-1)", "qkv", "o", "gate|up"]
-lab = ["entry", "setup", "upstream", "tile0", "mainloop", "s5", "s6", "s7", "exit", "smid", "s10", "s11", "s12"]
+ver = info[-(64 * 4 + 1):]
+names = ["g0", "g1", "g2", "g3"]   # launch order inside a layer: QKV, O, gate|up, down (identify by CTA count)
+lab = ["entry", "setup", "upstream", "tile0", "mainloop", "bar1", "scatter", "bar2", "exit", "smid", "owner", "qkv-ep", "s12"]
 NS = 13
 for which, part in (("verify", ver), ("draft", info[: 28 * 4 + 1])):
     nl = (len(part) - 1) // 4
