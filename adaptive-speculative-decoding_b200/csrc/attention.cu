@@ -104,6 +104,7 @@ struct AttnArgs {
     const int* seq_slot;           // [nseq]
     const int* page_table;
     int max_pages, nh, nkv, page_size, split_keys, nsplit_max, rg_count, kg_count;
+    int page_shift;                // log2(page_size) when it is a power of two, else -1 (division fallback)
     float scale_log2;
     float* o_part;                 // [M, nh, nsplit_max, hd]
     float* ml_part;                // [M, nh, nsplit_max, 2]
@@ -174,8 +175,10 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
             const int j = j0 + r;
             const bool ok = j < kend;
             const int jj = ok ? j : kbeg;
-            const int page = s_pt[jj / a.page_size - page0];
-            const size_t off = (((size_t)page * a.nkv + g) * a.page_size + jj % a.page_size) * HD;
+            const int pidx = a.page_shift >= 0 ? jj >> a.page_shift : jj / a.page_size;
+            const int pin = a.page_shift >= 0 ? jj & (a.page_size - 1) : jj - pidx * a.page_size;
+            const int page = s_pt[pidx - page0];
+            const size_t off = (((size_t)page * a.nkv + g) * a.page_size + pin) * HD;
             const uint32_t drow = (uint32_t)(buf * kKeyTile * ROWB + r * ROWB);
 #pragma unroll
             for (int cc = 0; cc < CH / 4; ++cc) {
@@ -256,16 +259,33 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
             }
             const int jbase = kbeg + tile * kKeyTile + key0 + (lane & 3) * 2;
             float tm0 = -INFINITY, tm1 = -INFINITY;
+            // tiles that end at or before the first new position are visible to every query row: no causal / length
+            // mask (only the rows past R stay masked)
+            const bool interior = kbeg + (tile + 1) * kKeyTile <= old_keys + 1;
+            if (interior) {
+                const float sc0 = r0 < R ? a.scale_log2 : -INFINITY, sc1 = r1 < R ? a.scale_log2 : -INFINITY;
 #pragma unroll
-            for (int i = 0; i < NT; ++i) {
+                for (int i = 0; i < NT; ++i) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = jbase + i * 8 + e;
-                    const bool in = j < kend;
-                    s[i][e] = (in && r0 < R && j <= qpos0) ? s[i][e] * a.scale_log2 : -INFINITY;
-                    s[i][2 + e] = (in && r1 < R && j <= qpos1) ? s[i][2 + e] * a.scale_log2 : -INFINITY;
-                    tm0 = fmaxf(tm0, s[i][e]);
-                    tm1 = fmaxf(tm1, s[i][2 + e]);
+                    for (int e = 0; e < 2; ++e) {
+                        s[i][e] = r0 < R ? s[i][e] * sc0 : -INFINITY;
+                        s[i][2 + e] = r1 < R ? s[i][2 + e] * sc1 : -INFINITY;
+                        tm0 = fmaxf(tm0, s[i][e]);
+                        tm1 = fmaxf(tm1, s[i][2 + e]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = jbase + i * 8 + e;
+                        const bool in = j < kend;
+                        s[i][e] = (in && r0 < R && j <= qpos0) ? s[i][e] * a.scale_log2 : -INFINITY;
+                        s[i][2 + e] = (in && r1 < R && j <= qpos1) ? s[i][2 + e] * a.scale_log2 : -INFINITY;
+                        tm0 = fmaxf(tm0, s[i][e]);
+                        tm1 = fmaxf(tm1, s[i][2 + e]);
+                    }
                 }
             }
             tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
@@ -513,6 +533,9 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     a.nh = L.nh;
     a.nkv = L.nkv;
     a.page_size = L.page_size;
+    a.page_shift = -1;
+    for (int b = 0; b < 16; ++b)
+        if ((1 << b) == L.page_size) a.page_shift = b;
     a.split_keys = L.split_keys;
     a.nsplit_max = L.nsplit_max;
     a.rg_count = rg;
