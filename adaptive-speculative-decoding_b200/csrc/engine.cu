@@ -294,6 +294,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             q.nkv = nkv;
             q.hd = hd;
             q.page_size = c.page_size;
+            gemm_set_next(P->o, &L.t_o);
             if (gemm_launch(P->qkv, L.t_qkv, P->x_norm, nullptr, e->nqkv, e->nqkv, e->pdl, s, false, &q,
                             consumer(e->sumsq)))
                 return -1;
@@ -337,15 +338,18 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             if (launch_attention(A, s)) return -1;
         }
         g_gemm_prefetch_next = 1;   // the O projection follows attention, which leaves HBM mostly idle
+        gemm_set_next(P->gu, &L.t_gu);
         if (project_residual(P->o, L.t_o, P->x_attn, L.ln2)) return -1;
         {
             PROF(PROF_GEMM);
+            gemm_set_next(P->down, &L.t_down);
             if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s, false, nullptr,
                             consumer(e->sumsq)))
                 return -1;
         }
         const bool last = l + 1 == c.n_layers;
         const __nv_bfloat16* wn = last ? e->final_norm : e->layers[l + 1].ln1;
+        if (!last) gemm_set_next(P->qkv, &e->layers[l + 1].t_qkv);
         if (project_residual(P->down, L.t_down, P->x_act, (last && n_logit_rows == 0 && !fn) ? nullptr : wn)) return -1;
     }
     if (n_logit_rows <= 0) return 0;
@@ -579,6 +583,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "early_trigger")) g_gemm_early_trigger = value;
     else if (!strcmp(name, "headroom")) g_gemm_headroom = value;
     else if (!strcmp(name, "recv_dedicated")) g_gemm_recv_dedicated = value;
+    else if (!strcmp(name, "next_prefetch_mb")) g_gemm_next_mb = value;
     else if (!strcmp(name, "tp_fused")) e->tp_fused = value;
     else if (!strcmp(name, "tp_two_shot")) e->tp_two_shot = value;
     else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;

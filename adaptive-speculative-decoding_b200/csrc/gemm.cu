@@ -53,6 +53,9 @@ struct GemmArgs {
     int l2_prefetch;    // k-blocks of weights (beyond the smem ring) each CTA pulls into L2 before the PDL wait
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
     NormFusion norm;
+    // L2 prefetch of the NEXT GEMM's weights, issued when this CTA has issued its own last tile: HBM would idle
+    // through this kernel's tail (cluster reduction, epilogue) and the next kernel's head otherwise
+    int next_ntiles, next_ksplit, next_kblocks, next_kp;   // next_kp = k-blocks per next-kernel CTA to prefetch (0 = off)
     TpFusion tp;        // world > 1: all-reduce over peer memory inside the owner epilogue
     unsigned long long* trace;  // diagnostics: kTraceSlots globaltimer stamps per CTA (nullptr = off)
 };
@@ -69,8 +72,26 @@ __device__ __forceinline__ void trace_stamp(const GemmArgs& a, int slot) {
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.0f + __expf(-g)) * u; }
 
+// L2 prefetch of the next kernel's weights: boxes k-block-major (the first k-block of every next CTA first), dealt
+// round-robin over this grid's CTAs and `nissue` issuing threads per CTA (this thread is number `who`)
+__device__ __forceinline__ void prefetch_next_weights(const GemmArgs& a, const CUtensorMap* tmap_next, int who, int nissue) {
+    const int ncta_next = a.next_ntiles * a.next_ksplit, nbox = ncta_next * a.next_kp;
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int nthr = gridDim.x * gridDim.y * gridDim.z * nissue;
+    const int nbase = a.next_kblocks / a.next_ksplit, nrem = a.next_kblocks % a.next_ksplit;
+    for (int b = cta * nissue + who; b < nbox; b += nthr) {
+        const int j = b / ncta_next, c = b - j * ncta_next;
+        const int nt = c % a.next_ntiles, ns = c / a.next_ntiles;
+        const int nkb_c = nbase + (ns < nrem ? 1 : 0);
+        if (j >= nkb_c) continue;
+        const int kb = ns * nbase + (ns < nrem ? ns : nrem) + j;
+        tma_prefetch_l2_2d(tmap_next, kb * kBlockK, nt * kTileN);
+    }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                                 const __grid_constant__ CUtensorMap tmap_x,
+                                                                const __grid_constant__ CUtensorMap tmap_next,
                                                                 const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-byte aligned: align the tile ring to 1024 by hand
@@ -199,6 +220,10 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
             }
         }
         if (nkb == 0 && lane == 0) mbar_arrive(tmem_full);
+        if (!a.reduce && a.next_kp > 0 && lane < 4) {   // no cluster phase: prefetch once this CTA's MMAs are done
+            mbar_wait(tmem_full, 0);
+            prefetch_next_weights(a, &tmap_next, lane, 4);
+        }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -410,6 +435,8 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
         if (threadIdx.x == 64) trace_stamp(a, 6);
         cluster_sync();
         if (threadIdx.x == 64) trace_stamp(a, 7);
+        // every CTA of the cluster has streamed its weights: HBM idles from here to the next kernel's first tile
+        if (warp == 1 && lane < 4 && a.next_kp > 0) prefetch_next_weights(a, &tmap_next, lane, 4);
         const float* recv = reinterpret_cast<const float*>(recv_base);
         const float4* recv4 = reinterpret_cast<const float4*>(recv_base);
         if (warp >= 2 && vec) {
@@ -635,6 +662,9 @@ int g_gemm_resid_prefetch = 1;
 int g_gemm_early_trigger = 0;
 int g_gemm_headroom = 1;
 int g_gemm_recv_dedicated = 1;
+NextPrefetch g_gemm_next;        // set by the caller right before gemm_launch, consumed by it
+int g_gemm_next_mb = 0;          // L2 budget (MB) for the next kernel's weights (engine option "next_prefetch_mb"); off:
+                                 // measured neutral after the cluster barrier, -3..-6 % when issued before it
 unsigned long long* g_gemm_trace = nullptr;   // diagnostics buffer [max launches][kTraceCtas][kTraceSlots]
 int g_gemm_trace_max = 0, g_gemm_trace_next = 0;
 constexpr int kTraceCtas = 1024;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
@@ -740,6 +770,21 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     return 0;
 }
 
+void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w) {
+    g_gemm_next = NextPrefetch{};
+    if (g_gemm_next_mb <= 0 || next_w == nullptr || next.m_tiles != 1) return;
+    const long long ncta = (long long)next.n_tiles * next.ksplit;
+    int kp = (int)(((long long)g_gemm_next_mb << 20) / (ncta * kABytes));
+    const int per_cta = (next.kblocks + next.ksplit - 1) / next.ksplit;
+    if (kp > per_cta) kp = per_cta;
+    if (kp <= 0) return;
+    g_gemm_next.tmap = next_w;
+    g_gemm_next.ntiles = next.n_tiles;
+    g_gemm_next.ksplit = next.ksplit;
+    g_gemm_next.kblocks = next.kblocks;
+    g_gemm_next.kp = kp;
+}
+
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
                 int n_valid, bool pdl, cudaStream_t stream, bool accumulate, const QkvEpilogue* qkv,
                 const NormFusion* norm, const TpFusion* tp) {
@@ -771,6 +816,16 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     g_gemm_prefetch_next = 0;
     a.norm = norm ? *norm : NormFusion{};
     a.tp = TpFusion{};
+    a.next_ntiles = a.next_ksplit = a.next_kblocks = a.next_kp = 0;
+    const CUtensorMap* tnext = &tmap_w;
+    if (g_gemm_next.kp > 0 && g_gemm_next.tmap != nullptr) {
+        a.next_ntiles = g_gemm_next.ntiles;
+        a.next_ksplit = g_gemm_next.ksplit;
+        a.next_kblocks = g_gemm_next.kblocks;
+        a.next_kp = g_gemm_next.kp;
+        tnext = g_gemm_next.tmap;
+    }
+    g_gemm_next = NextPrefetch{};
     if (tp && tp->world > 1) {
         if (!pl.reduce || pl.mode != GEMM_OUT_F32 || ((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
             return set_error("gemm: the fused all-reduce needs the cluster reduction on 16-byte aligned rows");
@@ -820,7 +875,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    ASD_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel, tmap_w, tmap_x, a));
+    ASD_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel, tmap_w, tmap_x, *tnext, a));
     count_launch(1);
     return 0;
 }

@@ -58,6 +58,15 @@ struct GemmPlan {
     uint32_t tmem_cols;
 };
 
+// The next weight-streaming GEMM of the stream (see GemmArgs::next_*): filled by gemm_set_next() before a launch.
+struct NextPrefetch {
+    const CUtensorMap* tmap = nullptr;
+    int ntiles = 0, ksplit = 1, kblocks = 0, kp = 0;
+};
+extern NextPrefetch g_gemm_next;
+extern int g_gemm_next_mb;
+// prefetch budget -> k-blocks per CTA of `next`; call right before launching the GEMM that precedes `next`
+void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w);
 extern int g_gemm_l2_prefetch, g_gemm_prefetch_next, g_gemm_resid_prefetch, g_gemm_early_trigger, g_gemm_headroom, g_gemm_recv_dedicated;
 int gemm_token_tile(int M);
 // reduce = 1: the K splits of a tile form a thread-block cluster and reduce through DSMEM, so the fp32
