@@ -202,10 +202,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             PROF(PROF_GEMM);
             const uint32_t ep = e->tp_epoch;
             TpFusion tf;
-            for (int r = 0; r < c.tp_size; ++r) {
-                tf.recv[r] = const_cast<float*>(e->peer_buf[ep & 1][r]);
-                tf.flags[r] = e->peer_flags[r] + 64;     // fused flags live behind the 64 words of the all-reduce kernel
-            }
+            for (int r = 0; r < c.tp_size; ++r) tf.recv[r] = const_cast<float*>(e->peer_buf[ep & 1][r]);
             tf.rank = c.tp_rank;
             tf.world = c.tp_size;
             tf.epoch = ep;
@@ -250,8 +247,9 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             // It pays once bytes dominate: saved traffic (W-1 - 2 (W-1)/W) * M * hidden * 4 >= 16 MB per boundary
             // (72B, 576 tokens, TP4: 56 -> 28 MB per boundary).  tp_two_shot = 1 forces it, -1 disables it.
             const double payload = (double)M * h * 4.0, w1 = c.tp_size - 1;
-            const bool two = e->tp_two_shot == 1 ||
-                             (e->tp_two_shot == 0 && (w1 - 2.0 * w1 / c.tp_size) * payload >= 16.0 * (1 << 20));
+            const bool two = (e->tp_two_shot == 1 && M <= kTpRowFlags) ||
+                             (e->tp_two_shot == 0 && M <= kTpRowFlags &&
+                              (w1 - 2.0 * w1 / c.tp_size) * payload >= 16.0 * (1 << 20));
             const float* bc[8] = {};
             uint32_t* rf[8] = {};
             for (int r = 0; r < c.tp_size; ++r) {
@@ -337,7 +335,6 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             PROF(PROF_ATTN);
             if (launch_attention(A, s)) return -1;
         }
-        g_gemm_prefetch_next = 1;   // the O projection follows attention, which leaves HBM mostly idle
         gemm_set_next(P->gu, &L.t_gu);
         if (project_residual(P->o, L.t_o, P->x_attn, L.ln2)) return -1;
         {
@@ -427,8 +424,9 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
     if (ok && cudaMemset(e->tickets, 0, Mx * c.n_kv_heads * 4) != cudaSuccess) ok = false;
     if (c.tp_size > 1) {
         // receive buffers of the fused GEMM + all-reduce: one [Mx, hidden] fp32 slot per source rank (the separate
-        // all-reduce kernel only uses slot 0); flags: 64 words for that kernel + [kTpFlagSlots][8] for the fused path
-        const size_t flag_bytes = 256 + (size_t)kTpFlagSlots * 8 * 4;
+        // all-reduce kernel uses slot 0 for the partial and slot 1 for the two-shot final rows); flags: 64 words of
+        // per-rank epochs + kTpRowFlags per-row epochs (two-shot)
+        const size_t flag_bytes = 256 + (size_t)kTpRowFlags * 4;
         alloc((void**)&e->tp_buf[0], (size_t)c.tp_size * Mx * c.hidden * 8);   // {value, epoch} word pairs
         alloc((void**)&e->tp_buf[1], (size_t)c.tp_size * Mx * c.hidden * 8);
         if (ok) {
@@ -578,8 +576,6 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
     else if (!strcmp(name, "attn_wide")) g_attn_wide = value;
     else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
-    else if (!strcmp(name, "l2_prefetch")) g_gemm_l2_prefetch = value;
-    else if (!strcmp(name, "resid_prefetch")) g_gemm_resid_prefetch = value;
     else if (!strcmp(name, "early_trigger")) g_gemm_early_trigger = value;
     else if (!strcmp(name, "headroom")) g_gemm_headroom = value;
     else if (!strcmp(name, "recv_dedicated")) g_gemm_recv_dedicated = value;

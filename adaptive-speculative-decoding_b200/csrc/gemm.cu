@@ -49,8 +49,6 @@ struct GemmArgs {
     int accumulate;     // fp32 output is added to what is already there (fused residual add)
     int recv_dedicated; // small token tiles: the DSMEM receive buffer has its own smem, so no barrier before the scatter
     int early_trigger;  // issue griddepcontrol.launch_dependents at kernel start instead of after the main loop
-    int resid_prefetch; // owner loads the old residual before the cluster barriers
-    int l2_prefetch;    // k-blocks of weights (beyond the smem ring) each CTA pulls into L2 before the PDL wait
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
     NormFusion norm;
     // L2 prefetch of the NEXT GEMM's weights, issued when this CTA has issued its own last tile: HBM would idle
@@ -156,13 +154,6 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_ws_kernel(const __grid_c
             const int nprod = a.stages < 4 ? a.stages : 4;
             const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
             bool waited = false;
-            // L2 prefetch of this CTA's later weight tiles: free HBM bandwidth while the upstream kernel
-            // (attention, a floor-bound small GEMM) is still running; the ring loads below then hit L2
-            {
-                const int lim = nkb < a.stages + a.l2_prefetch ? nkb : a.stages + a.l2_prefetch;
-                for (int kb = a.stages + pidx; kb < lim; kb += nprod)
-                    tma_prefetch_l2_2d(&tmap_w, (kb0 + kb) * kBlockK, tile_n * kTileN);
-            }
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % a.stages, round = kb / a.stages;
                 if (s % nprod != pidx) continue;
@@ -656,9 +647,6 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
     return 0;
 }
 
-int g_gemm_l2_prefetch = 0;     // k-blocks per CTA (engine option "l2_prefetch"); applied to a launch only when
-int g_gemm_prefetch_next = 0;
-int g_gemm_resid_prefetch = 1;
 int g_gemm_early_trigger = 0;
 int g_gemm_headroom = 1;
 int g_gemm_recv_dedicated = 1;
@@ -810,10 +798,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.reduce = pl.reduce;
     a.recv_dedicated = pl.recv_dedicated;
     a.accumulate = accumulate ? 1 : 0;
-    a.resid_prefetch = g_gemm_resid_prefetch;
     a.early_trigger = g_gemm_early_trigger;
-    a.l2_prefetch = (pdl && g_gemm_prefetch_next) ? g_gemm_l2_prefetch : 0;
-    g_gemm_prefetch_next = 0;
     a.norm = norm ? *norm : NormFusion{};
     a.tp = TpFusion{};
     a.next_ntiles = a.next_ksplit = a.next_kblocks = a.next_kp = 0;
@@ -829,7 +814,6 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     if (tp && tp->world > 1) {
         if (!pl.reduce || pl.mode != GEMM_OUT_F32 || ((ldo | n_valid) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
             return set_error("gemm: the fused all-reduce needs the cluster reduction on 16-byte aligned rows");
-        if (pl.m_tiles * pl.n_tiles * pl.ksplit > kTpFlagSlots) return set_error("gemm: too many owner CTAs for the fused all-reduce");
         if ((size_t)pl.M * ldo > tp->slot_stride) return set_error("gemm: receive slot smaller than the output");
         a.tp = *tp;
     }

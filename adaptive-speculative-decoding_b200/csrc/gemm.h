@@ -29,10 +29,9 @@ struct NormFusion {
 // the peers' words carry this launch's epoch.  The all-reduce happens inside the GEMM epilogue, row by row, with no
 // separate collective launch.  Receive buffers alternate with the epoch parity: a peer can only be one fused GEMM
 // ahead (it needs my push of launch e+1 to finish it), so launch e+2 never overwrites rows I still read.
-constexpr int kTpFlagSlots = 4096;       // (flag words of the separate all-reduce kernel's successor; kept for layout)
+constexpr int kTpRowFlags = 4096;        // per-row flags of the two-shot all-reduce kernel (max tokens per forward)
 struct TpFusion {
     float* recv[8] = {};       // this launch's receive buffer of every rank: [world][2 * slot_stride] words (peer-mapped)
-    uint32_t* flags[8] = {};   // unused by the inline-flag protocol
     int rank = 0, world = 1;
     uint32_t epoch = 0;
     int* error = nullptr;      // set to 1 if a peer never showed up (bounded spin)
@@ -67,7 +66,7 @@ extern NextPrefetch g_gemm_next;
 extern int g_gemm_next_mb;
 // prefetch budget -> k-blocks per CTA of `next`; call right before launching the GEMM that precedes `next`
 void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w);
-extern int g_gemm_l2_prefetch, g_gemm_prefetch_next, g_gemm_resid_prefetch, g_gemm_early_trigger, g_gemm_headroom, g_gemm_recv_dedicated;
+extern int g_gemm_early_trigger, g_gemm_headroom, g_gemm_recv_dedicated;
 int gemm_token_tile(int M);
 // reduce = 1: the K splits of a tile form a thread-block cluster and reduce through DSMEM, so the fp32
 // output is final ([M][ldo], one slice) instead of one slice per split
