@@ -78,7 +78,7 @@ def config_dict(wl, n_gpus, extra=None):
     c = {"workload": f"{wl['draft'].name} draft -> {wl['target'].name} target, bf16, chain k={wl['k']}, batch {wl['B']}, "
                      f"prefix {wl['prefix']}, temperature {wl['T']}, random-init weights, synthetic prompts",
          "batch": wl["B"], "k": wl["k"], "prefix": wl["prefix"], "temperature": wl["T"],
-         "parallelism": "single-gpu" if n_gpus == 1 else f"target tp{n_gpus} (all-reduce fused into the row-parallel GEMM epilogues over NVLink peer memory), draft replicated",
+         "parallelism": "single-gpu" if n_gpus == 1 else (f"target tp{n_gpus} (" + ("all-reduce fused into the row-parallel GEMM epilogues over NVLink peer memory" if (n_gpus == 2 or (n_gpus - 1) * wl["B"] * (wl["k"] + 1) * wl["target"].hidden_size * 8 <= 5 << 20) else "one-kernel peer-memory all-reduce + residual + norm over NVLink") + "), draft replicated"),
          "l2": "inputs larger than L2 (64 GB of weights streamed per verify step; no flush needed)"}
     if extra:
         c.update(extra)
