@@ -140,11 +140,14 @@ ASD_API int asd_engine_set_kv(asd_engine_t* e, void* kv_pool, int num_pages, con
 /* comm: ncclComm_t; nccl_allreduce_fn: address of ncclAllReduce from the NCCL the process loaded.
  * Called (fp32 sum, in place) after the O and down projections when tp_size > 1. */
 ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_allreduce_fn);
-/* Fused tensor-parallel boundary over NVLink peer memory (preferred to the NCCL path above): every rank
- * exports CUDA-IPC handles of its two partial buffers and its flag array (3 x 64 bytes), the host
- * all-gathers them (rank-major, world x 3 x 64 bytes) and each rank imports the table.  From then on the O /
- * down projections are followed by ONE kernel that all-reduces through P2P loads, adds the residual and emits
- * the norm statistics.  asd_engine_tp_error returns 1 if a peer ever failed to show up within the spin bound. */
+/* Tensor-parallel boundary over NVLink peer memory (preferred to the NCCL path above): every rank exports
+ * CUDA-IPC handles of its two receive buffers and its flag array (3 x 64 bytes), the host all-gathers them
+ * (rank-major, world x 3 x 64 bytes) and each rank imports the table.  From then on the O / down projections
+ * either finish the all-reduce inside their own epilogue (owner CTAs push {value, epoch} words into the peers'
+ * receive buffers; option "tp_fused", default at 2 ranks / small exchanges) or are followed by ONE kernel that
+ * all-reduces through P2P loads (one-shot, or two-shot with a home rank per row: option "tp_two_shot"), adds the
+ * residual and emits the norm statistics.  All paths give bit-identical residuals on every rank.
+ * asd_engine_tp_error returns 1 if a peer ever failed to show up within the spin bound. */
 ASD_API int asd_engine_ipc_export(asd_engine_t* e, void* handles_out);
 ASD_API int asd_engine_ipc_import(asd_engine_t* e, const void* all_handles);
 ASD_API int asd_engine_tp_error(asd_engine_t* e);
@@ -153,7 +156,11 @@ ASD_API int asd_engine_tp_error(asd_engine_t* e);
  * kernels), "fuse_rope" (1: bias + RoPE + q store + paged K/V append in the QKV GEMM epilogue),
  * "fuse_norm" (1: RMSNorm fused into the GEMMs: the O / down epilogues emit bf16(resid * ln_w) and the
  * per-token sum of squares, the consuming QKV / gate|up / lm_head epilogues apply rstd),
- * "attn_target_ctas", "glue_pdl", "ksplit", "stages" (0 = automatic), "profile" (0/1) */
+ * "attn_target_ctas", "attn_min_split_keys" (keys per flash-decoding split, default 1024), "glue_pdl",
+ * "ksplit", "stages" (0 = automatic), "headroom" (shared memory left for the next kernel's CTAs on <= 32-token
+ * tiles), "recv_dedicated", "early_trigger", "next_prefetch_mb" (tuning knobs),
+ * "tp_fused" (0 never, 1 where it pays, 2 always), "tp_two_shot" (-1 never, 0 where it pays, 1 always), "p2p",
+ * "profile" (0/1) */
 ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
 /* With option "profile" = 1 every launch is bracketed by CUDA events on the launching stream;
  * this call synchronises and returns the summed milliseconds and launch counts by kernel class
