@@ -20,7 +20,7 @@ def install_as_src():
     import sys
     import types
     names = ["algorithms", "algorithms.dp_solver", "algorithms.optimizer", "models", "models.stage", "models.predictor", "serving",
-             "serving.pipeline", "serving.cache_manager", "serving.real_model_pipeline", "theory",
+             "serving.pipeline", "serving.cache_manager", "serving.real_model_pipeline", "serving.server", "theory",
              "theory.optimal_stopping"]
     root = sys.modules.setdefault("src", types.ModuleType("src"))
     root.__path__ = []

@@ -206,3 +206,55 @@ def test_training_feature_vector_matches_the_reference_layout(tmp_path):
                                               "completion_tokens"}
     stats = json.load(open(tmp_path / "feature_stats.json"))
     assert set(stats) == {"mean", "std", "min", "max"} and len(stats["mean"]) == 64
+
+
+def test_http_server_mirrors_the_reference_endpoints():
+    """same routes, schemas, validation bounds and status codes as src/serving/server.py:223-376"""
+    from fastapi.testclient import TestClient
+    from asd_b200.serving.server import create_app
+
+    # before the pipeline exists every pipeline endpoint answers 503, /cache_stats 404, /health works
+    cold = TestClient(create_app(None))
+    assert cold.get("/health").json()["status"] == "healthy"
+    for method, path, body in (("post", "/generate", {"prompt": "x"}), ("get", "/stats", None),
+                               ("post", "/reset_stats", None), ("get", "/models", None),
+                               ("post", "/update_lambda", {"lambda_value": 2.0}),
+                               ("post", "/batch_generate", {"prompts": ["a"]})):
+        r = getattr(cold, method)(path, json=body) if body is not None else getattr(cold, method)(path)
+        assert r.status_code == 503, (path, r.status_code)
+    assert cold.get("/cache_stats").status_code == 404
+
+    cache = KVCacheManager(max_cache_size_gb=1, cleanup_interval=3600)
+    pipe = AdaptiveSpeculativePipeline(FakeManager(), SeqPredictor([0.2, 0.9]), None,
+                                       PipelineConfig(lambda_value=50.0, enable_caching=False), cache_manager=cache)
+    c = TestClient(create_app(pipe, cache))
+    r = c.post("/generate", json={"prompt": "What is the capital of France?", "max_tokens": 8, "request_id": "r-1"})
+    assert r.status_code == 200
+    body = r.json()
+    assert set(body) == {"request_id", "output", "stopped_at_stage", "latency_ms", "stage_probabilities",
+                         "stage_costs", "total_tokens", "tokens_per_second", "cache_hits"}
+    assert body["request_id"] == "r-1" and body["output"]
+    # validation bounds of the reference schemas (422 from pydantic)
+    assert c.post("/generate", json={"prompt": "x", "max_tokens": 0}).status_code == 422
+    assert c.post("/generate", json={"prompt": "x", "temperature": 2.5}).status_code == 422
+    assert c.post("/update_lambda", json={"lambda_value": 0.001}).status_code == 422
+    rb = c.post("/batch_generate", json={"prompts": ["a", "b", "c"], "max_tokens": 4})
+    assert rb.status_code == 200 and len(rb.json()["results"]) == 3
+    st = c.get("/stats").json()
+    assert st["total_requests"] == 4 and abs(sum(st["stage_distribution"]) - 1.0) < 1e-9
+    up = c.post("/update_lambda", json={"lambda_value": 2.5}).json()
+    assert up == {"message": "Lambda updated successfully", "old_lambda": 50.0, "new_lambda": 2.5}
+    assert pipe.lambda_value == 2.5
+    assert c.post("/reset_stats").json() == {"message": "Statistics reset successfully"}
+    assert c.get("/stats").json()["total_requests"] == 0
+    models = c.get("/models").json()["models"]
+    assert set(models) == {"8b", "13b", "34b", "70b"} and all("error" in v for v in models.values())  # fakes have no info
+    assert "total_entries" in c.get("/cache_stats").json() or c.get("/cache_stats").status_code == 200
+
+    class Boom(FakeManager):
+        def get_stage(self, name):
+            raise RuntimeError("stage exploded")
+    bad = AdaptiveSpeculativePipeline(Boom(), SeqPredictor([0.5]), None, PipelineConfig(enable_caching=False))
+    r = TestClient(create_app(bad)).post("/generate", json={"prompt": "x"})
+    assert r.status_code == 500 and "stage exploded" in r.json()["detail"]
+    cache.shutdown()
