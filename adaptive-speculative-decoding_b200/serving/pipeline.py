@@ -139,6 +139,18 @@ class AdaptiveSpeculativePipeline:
         return await loop.run_in_executor(self.executor, self.process_request, prompt, max_tokens, temperature,
                                           request_id)
 
+    def _decide(self, probabilities: List[float], costs: List[float], stage_idx: int, n_stages: int,
+                all_costs: Optional[List[float]]):
+        """stop / escalate after stage `stage_idx`; returns (stop, k_star)."""
+        if self.config.reference_compat:   # the reference's loop: DP on the prefix seen so far (:248-256)
+            k_star, _ = optimal_stopping_rule(p=probabilities[:stage_idx + 1], C=costs[:stage_idx + 1],
+                                              lam=self.config.lambda_value, risk_adjustment=False)
+            return k_star == stage_idx, k_star
+        # the documented rule: DP over ALL stages, unseen stages at probability 1.0
+        full_p = probabilities + [1.0] * (n_stages - len(probabilities))
+        k_full, _ = optimal_stopping_rule(p=full_p, C=all_costs, lam=self.config.lambda_value, risk_adjustment=False)
+        return k_full <= stage_idx, stage_idx
+
     # -- pipeline.py:165-286
     def _process_stages(self, request_id: str, prompt: str, max_tokens: int, temperature: float,
                         start_time: float) -> RequestResult:
@@ -181,16 +193,7 @@ class AdaptiveSpeculativePipeline:
                 probabilities.append(prob)
             else:
                 probabilities.append(1.0)                                                # :241-242
-            if compat:   # the reference's loop: DP on the prefix seen so far (:248-256)
-                k_star, _ = optimal_stopping_rule(p=probabilities[:stage_idx + 1], C=costs[:stage_idx + 1],
-                                                  lam=self.config.lambda_value, risk_adjustment=False)
-                stop = k_star == stage_idx
-            else:        # the documented rule: DP over ALL stages, unseen stages at probability 1.0
-                full_p = probabilities + [1.0] * (len(stage_names) - len(probabilities))
-                k_full, _ = optimal_stopping_rule(p=full_p, C=all_costs, lam=self.config.lambda_value,
-                                                  risk_adjustment=False)
-                stop = k_full <= stage_idx
-                k_star = stage_idx
+            stop, k_star = self._decide(probabilities, costs, stage_idx, len(stage_names), all_costs)
             if stop:
                 break
             if stage_idx < len(stage_names) - 1:
@@ -217,9 +220,70 @@ class AdaptiveSpeculativePipeline:
             if i < len(st["avg_stage_probabilities"]):
                 st["avg_stage_probabilities"][i] = (1 - alpha) * st["avg_stage_probabilities"][i] + alpha * prob
 
-    # -- pipeline.py:314-338 (sequential, as in the reference)
-    def batch_process(self, prompts: List[str], max_tokens: int = 512, temperature: float = 0.7) -> List[RequestResult]:
-        return [self.process_request(p, max_tokens, temperature) for p in prompts]
+    # -- pipeline.py:314-338 (sequential, as in the reference) + the batching its TODO at :331 asks for
+    def batch_process(self, prompts: List[str], max_tokens: int = 512, temperature: float = 0.7,
+                      batched: bool = False) -> List[RequestResult]:
+        """`batched=False`: one request after the other, exactly like the reference.  `batched=True`: the requests
+        walk the cascade together - every stage makes ONE `generate` call for all requests still alive, which is
+        what fills the engine's batch dimension; each request keeps its own probabilities, costs and stop decision
+        (same rule as `_process_stages`).  Differences to the sequential loop: no per-(request, stage) blob cache,
+        and the Bayesian n_obs is the request count before the batch for all of its members."""
+        if not batched:
+            return [self.process_request(p, max_tokens, temperature) for p in prompts]
+        start = time.time()
+        names = self._stage_names()
+        all_costs = None if self.config.reference_compat else [self.stage_manager.get_stage(n).cost_per_token for n in names]
+        n_obs = max(100, self.stats["total_requests"])
+        st = [dict(rid=str(uuid.uuid4()), prompt=p, cur=p, probs=[], costs=[], outs=[], tokens=0, k=None)
+              for p in prompts]
+        for s_ in st:
+            self.active_requests[s_["rid"]] = {"start_time": start, "prompt": s_["prompt"][:100]}
+        try:
+            live = list(range(len(st)))
+            for stage_idx, name in enumerate(names):
+                if not live:
+                    break
+                stage = self.stage_manager.get_stage(name)
+                texts, logprobs, _ = stage.generate(prompts=[st[i]["cur"] for i in live], max_tokens=max_tokens,
+                                                    temperature=temperature, return_logprobs=True)
+                nxt = []
+                for j, i in enumerate(live):
+                    r = st[i]
+                    r["outs"].append(texts[j])
+                    r["costs"].append(stage.cost_per_token)
+                    r["tokens"] += len(texts[j].split())
+                    if stage_idx < len(names) - 1:
+                        lp = logprobs[j] if len(logprobs) > j else None
+                        prob = self.predictor.predict(prompt=r["cur"], draft_output=texts[j], draft_logprobs=lp,
+                                                      stage_id=stage_idx, feature_extractor=self.feature_extractor)
+                        if self.config.risk_adjustment:
+                            prob = bayesian_adjustment(prob, n_obs, self.config.risk_alpha, self.config.risk_beta)
+                        r["probs"].append(prob)
+                    else:
+                        r["probs"].append(1.0)
+                    stop, k_star = self._decide(r["probs"], r["costs"], stage_idx, len(names), all_costs)
+                    if stop or stage_idx == len(names) - 1:
+                        r["k"] = k_star
+                    else:
+                        r["cur"] = r["prompt"] + " " + texts[j]
+                        nxt.append(i)
+                live = nxt
+            results = []
+            for r in st:
+                ms = (time.time() - start) * 1000
+                res = RequestResult(request_id=r["rid"], output=r["outs"][r["k"]], stopped_at_stage=r["k"], latency_ms=ms,
+                                    stage_probabilities=r["probs"], stage_costs=r["costs"][:r["k"] + 1], cache_hits=0,
+                                    total_tokens=r["tokens"], tokens_per_second=r["tokens"] / (ms / 1000) if ms > 0 else 0)
+                self._update_stats(res)
+                results.append(res)
+            return results
+        except Exception as e:
+            logger.error(f"Batch of {len(prompts)} requests failed: {e}")
+            self.stats["error_count"] += 1
+            raise
+        finally:
+            for s_ in st:
+                self.active_requests.pop(s_["rid"], None)
 
     def update_lambda(self, new_lambda: float):
         old = self.config.lambda_value

@@ -258,3 +258,27 @@ def test_http_server_mirrors_the_reference_endpoints():
     r = TestClient(create_app(bad)).post("/generate", json={"prompt": "x"})
     assert r.status_code == 500 and "stage exploded" in r.json()["detail"]
     cache.shutdown()
+
+
+def test_batched_cascade_matches_the_sequential_decisions():
+    """batch_process(batched=True): one generate call per stage for all live requests, same per-request decisions"""
+    class ByPrompt:
+        def predict(self, prompt, draft_output, draft_logprobs, stage_id, feature_extractor=None):
+            base = {"easy": 0.97, "mid": 0.55, "hard": 0.05}[prompt.split()[0]]
+            return min(0.99, base + 0.2 * stage_id)
+    prompts = ["easy one", "hard two", "mid three", "hard four", "easy five"]
+    cfg = dict(lambda_value=20.0, enable_caching=False, risk_adjustment=False)
+    seq_mgr, bat_mgr = FakeManager(), FakeManager()
+    seq = AdaptiveSpeculativePipeline(seq_mgr, ByPrompt(), None, PipelineConfig(**cfg)).batch_process(prompts, 8)
+    bat_pipe = AdaptiveSpeculativePipeline(bat_mgr, ByPrompt(), None, PipelineConfig(**cfg))
+    bat = bat_pipe.batch_process(prompts, 8, batched=True)
+    assert [r.stopped_at_stage for r in bat] == [r.stopped_at_stage for r in seq]
+    assert [r.output for r in bat] == [r.output for r in seq]
+    assert [r.stage_probabilities for r in bat] == [r.stage_probabilities for r in seq]
+    assert [r.stage_costs for r in bat] == [r.stage_costs for r in seq]
+    assert len(set(r.stopped_at_stage for r in bat)) > 1            # the batch really splits across stages
+    # one generate call per stage that still had live requests, instead of one per (request, stage)
+    assert [bat_mgr.stages[n].calls for n in bat_mgr.stage_names()] == [1 if any(r.stopped_at_stage >= i for r in bat) else 0
+                                                                        for i in range(4)]
+    assert sum(s.calls for s in seq_mgr.stages.values()) == sum(r.stopped_at_stage + 1 for r in seq)
+    assert bat_pipe.get_stats()["total_requests"] == 5 and not bat_pipe.active_requests
