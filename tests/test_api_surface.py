@@ -282,3 +282,41 @@ def test_batched_cascade_matches_the_sequential_decisions():
                                                                         for i in range(4)]
     assert sum(s.calls for s in seq_mgr.stages.values()) == sum(r.stopped_at_stage + 1 for r in seq)
     assert bat_pipe.get_stats()["total_requests"] == 5 and not bat_pipe.active_requests
+
+
+def test_predictor_training_on_saved_rows(tmp_path):
+    """rows written by save_training_data train the reference's MLP recipe (K-fold, AdamW, MSE)"""
+    import json
+    import torch
+    from asd_b200.training.generate_training_data import TrainingSample, extract_features, save_training_data
+    from asd_b200.training.train_predictor import ResearchQualityPredictor, load_training_rows, train_quality_predictor
+    rng = np.random.default_rng(0)
+    samples = []
+    for i in range(240):
+        lps = (-rng.random(12) * (0.2 + 3.0 * rng.random())).tolist()
+        prompt, out = "what is " + "x " * int(rng.integers(1, 9)), "tok " * int(rng.integers(2, 20))
+        feats = extract_features(prompt, out, {"logprobs": lps, "generation_time": 0.1, "completion_tokens": 12}, i % 4)
+        q = float(1.0 / (1.0 + np.exp(-(3.0 + 2.0 * np.mean(lps)))))            # quality follows the mean logprob
+        samples.append(TrainingSample(prompt, i % 4, out, "", feats, float(q >= 0.7), q, 0.1, 3, 12))
+    path = save_training_data(samples, str(tmp_path))
+    X, y = load_training_rows(path)
+    assert X.shape == (240, 64) and y.shape == (240,)
+    cfg = {"predictor": {"model": {"input_dim": 64, "hidden_layers": [32, 16], "dropout": 0.0},
+                         "training": {"batch_size": 32, "num_epochs": 40, "learning_rate": 0.01}, "data": {"cv_folds": 3}}}
+    res = train_quality_predictor(X, y, cfg)
+    cv = res["cross_validation"]
+    assert set(cv) == {"mean_r2", "std_r2", "mean_mse", "std_mse", "fold_results"} and len(cv["fold_results"]) == 3
+    assert set(cv["fold_results"][0]) == {"fold", "r2_score", "mse", "mae", "best_val_loss"}
+    assert cv["mean_r2"] > 0.5, cv                                              # the relation is learnable
+    assert res["training_config"]["num_samples"] == 240 and res["model_config"]["architecture"] == "mlp"
+    m = ResearchQualityPredictor(64, [32, 16], 0.0)
+    m.load_state_dict(res["state_dict"])
+    m.eval()
+    xs = torch.from_numpy(((X - np.array(res["scaler"]["mean"])) / np.array(res["scaler"]["std"])).astype(np.float32))
+    with torch.no_grad():
+        p = m(xs).numpy()
+    assert float(((p - y) ** 2).mean()) < 0.02
+    assert len(ResearchQualityPredictor().network) == 3 * 4 + 2                 # 128 -> 256 -> 128 -> 64 -> 1
+    with pytest.raises(ValueError):
+        train_quality_predictor(X, y, {"predictor": {"model": {"input_dim": 128}}})
+    json.dumps({k: v for k, v in res.items() if k != "state_dict"})              # the report part is JSON-serialisable
