@@ -1,6 +1,6 @@
 // Paged-KV attention for the verify step: every (k+1) new position of a sequence is scored against
-// the paged prefix in ONE pass (causal among the new positions), split over the KV length
-// (flash-decoding) so that B x n_kv x splits CTAs keep HBM busy; a combine kernel merges splits.
+// the paged prefix in ONE pass (causal among the new positions); long contexts (>= 1024 keys per piece) are
+// split over the KV length (flash-decoding) and merged by the last CTA to finish.
 //
 //   * work item = (sequence, kv head, kv split).  The query tile is all new tokens x the GQA group
 //     of that kv head (rows = q_len * G, e.g. 6 x 5 = 30 for Qwen2.5-32B with k = 5), so each K/V
@@ -12,8 +12,12 @@
 //     64-key tile between them, then merge through shared memory, so that a CTA always has 4+ warps
 //     issuing loads; the last CTA of a (sequence, kv head) to finish merges the kv splits (atomic
 //     ticket), so there is no separate combine launch;
-//   * K/V were appended in place by qkv_rope_kernel before this kernel runs; rejected speculative
-//     positions are simply overwritten by the next step (rollback = not advancing the length).
+//   * programmatic dependent launch: the batch description, the CTA's slice of the page table (staged in
+//     shared memory) and the K/V tiles of keys older than this step's tokens are fetched BEFORE
+//     griddepcontrol.wait, i.e. while the QKV GEMM upstream is still in its epilogue;
+//   * K/V were appended in place by the QKV GEMM's epilogue (or qkv_rope_kernel on the unfused path) before
+//     this kernel's wait returns; rejected speculative positions are simply overwritten by the next step
+//     (rollback = not advancing the length).
 // attn_simple_kernel is a one-warp-per-(token, head) restatement used to cross-check the tensor-core
 // kernel on the device (engine option attn_impl = 0).
 //

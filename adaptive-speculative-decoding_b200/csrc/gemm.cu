@@ -7,14 +7,23 @@
 //     work is wasted on padding rows and one TMEM accumulator [128 lanes x MT columns] holds the tile;
 //   * both operands arrive by TMA (128-byte swizzle) into a multi-stage mbarrier ring; W with an
 //     L2 evict-first policy (read exactly once), X with evict-last (re-read by every CTA);
-//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-//     warps 2..5 = epilogue (tcgen05.ld -> registers -> global);
+//   * warp 0 = per-token rstd of the fused RMSNorm, warp 1 = TMEM allocator + single-thread tcgen05.mma
+//     issuer, warps 2..5 = TMA producers during the main loop (lane 0 of each owns the ring slots s % 4) and
+//     epilogue afterwards (tcgen05.ld -> registers);
 //   * grid = (weight tiles, K splits, token tiles); the host picks the split so that all CTAs are
 //     co-resident in ONE wave (2-3 CTAs/SM) - with HBM as the shared bottleneck every CTA then
-//     progresses at the same rate and there is no tail; split-K partials are fp32 slices that the
-//     consumer kernel (add+RMSNorm / RoPE) sums in a fixed order (deterministic, no atomics).
-// Epilogues: fp32 (partials / logits), bf16, and SwiGLU for the gate|up projection whose rows are
-// pre-interleaved (64 gate rows, 64 up rows per tile) so silu(g)*u never round-trips to HBM.
+//     progresses at the same rate and there is no tail;
+//   * the K splits of a tile form a thread-block cluster (1, ksplit, 1): CTA r owns the token columns
+//     [r*MT/ks, (r+1)*MT/ks), every CTA scatters those columns of its TMEM tile into the owner's idle tile
+//     ring through DSMEM, the owner adds the partials in rank order (deterministic, no atomics, no HBM round
+//     trip) and runs the epilogue for its tokens; without the cluster (option reduce = 0) the partials are fp32
+//     slices that the glue kernels sum.
+// Epilogues, all rolled 128-bit loops (a CTA runs its epilogue once: unrolled code is paid in instruction-cache
+// misses): fp32 (+ residual accumulate, + bf16(resid * ln_w) and per-token sum of squares for the fused RMSNorm,
+// + the tensor-parallel all-reduce over NVLink peer memory), QKV (rstd, bias, rotate-half RoPE, q store, paged
+// K/V append), bf16, SwiGLU for the gate|up projection whose rows are pre-interleaved (64 gate rows, 64 up rows
+// per tile) so silu(g)*u never round-trips to HBM, and fp32 logits * rstd for the lm_head.
+// Programmatic dependent launch: weight stages are issued before griddepcontrol.wait, activations after it.
 //
 // Stands behind Stage.generate's model forward, which the reference delegates to vLLM
 // (/root/reference/src/serving/real_model_pipeline.py:98-108,135).
@@ -51,8 +60,8 @@ struct GemmArgs {
     int early_trigger;  // issue griddepcontrol.launch_dependents at kernel start instead of after the main loop
     QkvEpilogue qkv;    // GEMM_OUT_QKV only
     NormFusion norm;
-    // L2 prefetch of the NEXT GEMM's weights, issued when this CTA has issued its own last tile: HBM would idle
-    // through this kernel's tail (cluster reduction, epilogue) and the next kernel's head otherwise
+    // optional L2 prefetch of the NEXT GEMM's weights from the idle MMA warp once this cluster has streamed its own
+    // (engine option next_prefetch_mb; measured neutral, off by default)
     int next_ntiles, next_ksplit, next_kblocks, next_kp;   // next_kp = k-blocks per next-kernel CTA to prefetch (0 = off)
     TpFusion tp;        // world > 1: all-reduce over peer memory inside the owner epilogue
     unsigned long long* trace;  // diagnostics: kTraceSlots globaltimer stamps per CTA (nullptr = off)
