@@ -170,11 +170,17 @@ def run_ours(args):
     emitted = torch.zeros((), dtype=torch.int64, device=dev)
     barrier()
     dec.time_verify, dec.verify_events = True, []
+    ncu_range = os.environ.get("ASD_NCU_RANGE") == "1"   # `ncu --profile-from-start off`: capture the timed steps only
+    if ncu_range:
+        torch.cuda.profiler.start()
     ev[0].record()
     for _ in range(args.steps):
         out = dec.step()
         emitted += (out["accepted_len"].to(torch.int64) + 1).sum()
     ev[1].record()
+    if ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     dec.time_verify = False
     verify_ms_timed = sorted(a.elapsed_time(b) for a, b in dec.verify_events)
