@@ -659,7 +659,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 int g_gemm_early_trigger = 0;
 int g_gemm_headroom = 1;
 int g_gemm_recv_dedicated = 1;
-NextPrefetch g_gemm_next;        // set by the caller right before gemm_launch, consumed by it
+thread_local NextPrefetch g_gemm_next;   // set by the caller right before gemm_launch, consumed by it (per host thread)
 int g_gemm_next_mb = 0;          // L2 budget (MB) for the next kernel's weights (engine option "next_prefetch_mb"); off:
                                  // measured neutral after the cluster barrier, -3..-6 % when issued before it
 unsigned long long* g_gemm_trace = nullptr;   // diagnostics buffer [max launches][kTraceCtas][kTraceSlots]

@@ -62,7 +62,7 @@ struct NextPrefetch {
     const CUtensorMap* tmap = nullptr;
     int ntiles = 0, ksplit = 1, kblocks = 0, kp = 0;
 };
-extern NextPrefetch g_gemm_next;
+extern thread_local NextPrefetch g_gemm_next;
 extern int g_gemm_next_mb;
 // prefetch budget -> k-blocks per CTA of `next`; call right before launching the GEMM that precedes `next`
 void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w);
