@@ -115,8 +115,10 @@ class QwenEngine:
         return {c: (ms[i], n[i]) for i, c in enumerate(self.PROFILE_CLASSES)}
 
     def enable_p2p(self, group=None):
-        """Exchange CUDA-IPC handles of the TP partial buffers with the other ranks (torch.distributed) and
-        switch the row-parallel boundaries to the fused peer-memory all-reduce kernel."""
+        """Exchange CUDA-IPC handles of the TP receive buffers with the other ranks (torch.distributed) and
+        switch the row-parallel boundaries to the peer-memory paths: the all-reduce inside the O / down GEMM
+        epilogues where it pays (2 ranks, small exchanges), else the one-kernel all-reduce + residual + norm
+        (options ``tp_fused`` / ``tp_two_shot``)."""
         import torch.distributed as dist
         mine = ctypes.create_string_buffer(3 * 64)
         check(lib().asd_engine_ipc_export(self.h, mine), "asd_engine_ipc_export")
