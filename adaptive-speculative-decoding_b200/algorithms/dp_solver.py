@@ -6,7 +6,9 @@ Results are bit-exact with the reference (tests/test_stop_rule.py)."""
 from __future__ import annotations
 
 import ctypes
+import functools
 import logging
+import operator
 from typing import List, Tuple
 
 import numpy as np
@@ -39,14 +41,13 @@ def optimal_stopping_rule(p: List[float], C: List[float], lam: float, risk_adjus
 
 
 def compute_expected_cost(p: List[float], C: List[float], lam: float, stopping_stage: int) -> float:
-    """dp_solver.py:74-103 (host bookkeeping; a handful of binary64 operations in the
-    reference's order)."""
-    p_bar = 1.0
-    for i in range(stopping_stage + 1):
-        p_bar *= p[i]
-    computation_cost = sum(C[:stopping_stage + 1])
-    quality_loss = lam * (1 - p_bar)
-    return computation_cost + quality_loss
+    """Expected cost of stopping at ``stopping_stage`` (dp_solver.py:74-103):
+    sum_{i<=k} C_i + lam * (1 - prod_{i<=k} p_i).  Left-to-right folds keep the reference's binary64
+    rounding (goldens: tests/golden/stop_rule_golden.json ``expected_cost``)."""
+    k = stopping_stage + 1
+    reach = functools.reduce(operator.mul, p[:k], 1.0)
+    spent = functools.reduce(operator.add, C[:k], 0)
+    return spent + lam * (1 - reach)
 
 
 def bayesian_adjustment(p_hat: float, n_obs: int, alpha: float = 1.0, beta: float = 1.0) -> float:
@@ -73,67 +74,133 @@ def stop_rule_batch(p, C, lam: float, risk_adjustment: bool = False, alpha: floa
     return k_star, J
 
 
+def stop_rule_rows(p, C, lam_rows, risk_adjustment: bool = False, alpha: float = 1.0, beta: float = 1.0):
+    """One library call for n independent stop decisions with one lambda per row.  numpy inputs ([n, L] float64,
+    lam [n]) run through ``asd_stop_rule_rows_host``; CUDA tensors through ``asd_stop_rule_rows`` on the device.
+    Returns (k_star int32 [n], J float64 [n, L+1]) of the same kind as the inputs."""
+    if isinstance(p, np.ndarray) or isinstance(p, (list, tuple)):
+        pa, ca, la = _arr(p), _arr(C), _arr(lam_rows)
+        if pa.shape != ca.shape or pa.ndim != 2 or la.shape != (pa.shape[0],):
+            raise ValueError("p and C must be [n, L] and lam [n]")
+        n, L = pa.shape
+        k = np.empty(n, dtype=np.int32)
+        J = np.empty((n, L + 1), dtype=np.float64)
+        if n:
+            check(lib().asd_stop_rule_rows_host(pa.ctypes.data, ca.ctypes.data, la.ctypes.data, n, L,
+                                                int(bool(risk_adjustment)), float(alpha), float(beta),
+                                                k.ctypes.data, J.ctypes.data), "asd_stop_rule_rows_host")
+        return k, J
+    import torch
+    assert p.is_cuda and p.dtype == torch.float64
+    p, C, lam_rows = p.contiguous(), C.contiguous(), lam_rows.contiguous()
+    n, L = p.shape
+    k = torch.empty(n, dtype=torch.int32, device=p.device)
+    J = torch.empty(n, L + 1, dtype=torch.float64, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = lib().asd_stop_rule_rows(p.data_ptr(), C.data_ptr(), lam_rows.data_ptr(), n, L, int(bool(risk_adjustment)),
+                                      float(alpha), float(beta), k.data_ptr(), J.data_ptr(),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    check(rc, "asd_stop_rule_rows")
+    return k, J
+
+
 class OptimalStoppingTable:
-    """dp_solver.py:133-210: memo of stop decisions keyed on probabilities rounded to 2 dp."""
+    """Memo of stop decisions (API of dp_solver.py:133-210: ``precompute(cost_ratios, prob_grid)``,
+    ``lookup(probabilities, lambda_value, fallback_to_dp)``, attributes ``lambda_values``, ``num_stages``,
+    ``table[lam][prob_key]``).  Where the reference runs one Python DP per (lambda, scenario), ``precompute``
+    here lays the whole lambda x grid product out as one [n, L] batch and evaluates it with a single library
+    call (``stop_rule_rows``), then files the answers under the reference's keys (probabilities rounded to 2 dp)."""
+
+    DEFAULT_COSTS = (1.0, 1.6, 4.2, 8.8)          # the fallback cost vector of dp_solver.py:205
 
     def __init__(self, lambda_values: List[float], num_stages: int = 4):
         self.lambda_values = lambda_values
         self.num_stages = num_stages
         self.table = {}
 
+    @staticmethod
+    def _key(probabilities) -> tuple:
+        return tuple(round(float(x), 2) for x in probabilities)
+
     def precompute(self, cost_ratios: List[float], prob_grid: List[List[float]]):
-        logger.info("Precomputing optimal stopping table...")
-        for lam in self.lambda_values:
+        lams = list(self.lambda_values)
+        for lam in lams:
             self.table[lam] = {}
-            for prob_scenario in prob_grid:
-                k_star, _ = optimal_stopping_rule(prob_scenario, cost_ratios, lam)
-                self.table[lam][tuple(round(p, 2) for p in prob_scenario)] = k_star
-        logger.info(f"Precomputed table for {len(self.lambda_values)} lambda values")
+        grid = [list(map(float, sc)) for sc in prob_grid]
+        if not grid or not lams:
+            return
+        by_len = {}
+        for sc in grid:                      # ragged grids are legal in the reference: batch per length
+            if len(sc) != len(cost_ratios):
+                raise ValueError("p and C must have the same length")
+            by_len.setdefault(len(sc), []).append(sc)
+        for L, rows in by_len.items():
+            if L == 0:
+                for lam in lams:
+                    self.table[lam][()] = -1
+                continue
+            P = np.tile(_arr(rows), (len(lams), 1))
+            Cm = np.broadcast_to(_arr(cost_ratios), P.shape)
+            lam_rows = np.repeat(_arr(lams), len(rows))
+            k_star, _ = stop_rule_rows(P, Cm, lam_rows)
+            keys = [self._key(sc) for sc in rows]
+            for li, lam in enumerate(lams):
+                base = li * len(rows)
+                # later scenarios overwrite earlier ones with the same rounded key, as in the reference's loop
+                self.table[lam].update(zip(keys, (int(x) for x in k_star[base:base + len(rows)])))
+        logger.info("optimal stopping table: %d lambdas x %d scenarios in %d batched call(s)", len(lams), len(grid),
+                    len(by_len))
 
     def lookup(self, probabilities: List[float], lambda_value: float, fallback_to_dp: bool = True) -> int:
-        closest_lam = min(self.lambda_values, key=lambda x: abs(x - lambda_value))
-        prob_key = tuple(round(p, 2) for p in probabilities)
-        if closest_lam in self.table and prob_key in self.table[closest_lam]:
-            return self.table[closest_lam][prob_key]
-        if fallback_to_dp:
-            logger.debug(f"Table miss for lambda={lambda_value}, computing DP")
-            cost_ratios = [1.0, 1.6, 4.2, 8.8][:len(probabilities)]      # dp_solver.py:205
-            k_star, _ = optimal_stopping_rule(probabilities, cost_ratios, lambda_value)
-            return k_star
-        return len(probabilities) - 1
+        nearest = min(self.lambda_values, key=lambda x: abs(x - lambda_value))
+        hit = self.table.get(nearest, {}).get(self._key(probabilities))
+        if hit is not None:
+            return hit
+        if not fallback_to_dp:
+            return len(probabilities) - 1
+        costs = list(self.DEFAULT_COSTS[:len(probabilities)])
+        return optimal_stopping_rule(probabilities, costs, lambda_value)[0]
 
 
 class AdaptiveStopping:
-    """dp_solver.py:213-289: Hoeffding / UCB bookkeeping around the stop rule (host statistics)."""
+    """Online per-stage reward statistics with Hoeffding bounds (API of dp_solver.py:213-289:
+    ``update_statistics``, ``get_confidence_bounds``, ``should_explore``; attributes ``lambda_value``,
+    ``confidence_level``, ``stage_counts``, ``stage_rewards``, ``total_steps``)."""
+
+    NUM_STAGES = 4
+    MIN_PULLS = 10          # every stage is explored at least this often
+    SLACK = 0.1             # a stage stays interesting while its upper bound is within SLACK of the best
 
     def __init__(self, initial_lambda: float = 1.0, confidence_level: float = 0.1):
         self.lambda_value = initial_lambda
         self.confidence_level = confidence_level
-        self.stage_counts = np.zeros(4)
-        self.stage_rewards = np.zeros(4)
+        self.stage_counts = np.zeros(self.NUM_STAGES)
+        self.stage_rewards = np.zeros(self.NUM_STAGES)
         self.total_steps = 0
 
     def update_statistics(self, chosen_stage: int, observed_quality: float, observed_latency: float):
-        self.stage_counts[chosen_stage] += 1
-        normalized_latency = observed_latency / 1000.0
-        reward = observed_quality - self.lambda_value * normalized_latency
-        n = self.stage_counts[chosen_stage]
-        self.stage_rewards[chosen_stage] = ((n - 1) * self.stage_rewards[chosen_stage] + reward) / n
+        reward = observed_quality - self.lambda_value * (observed_latency / 1000.0)     # latency in seconds
+        seen = self.stage_counts[chosen_stage]
+        # running mean in the reference's form ((n-1) * mean + reward) / n so the statistics agree to the last bit
+        self.stage_rewards[chosen_stage] = (seen * self.stage_rewards[chosen_stage] + reward) / (seen + 1.0)
+        self.stage_counts[chosen_stage] = seen + 1.0
         self.total_steps += 1
 
+    def _radius(self) -> np.ndarray:
+        with np.errstate(divide="ignore"):
+            return np.sqrt(-np.log(self.confidence_level / 2) / (2 * self.stage_counts))
+
     def get_confidence_bounds(self, stage: int) -> Tuple[float, float]:
-        n = self.stage_counts[stage]
-        if n == 0:
+        if self.stage_counts[stage] == 0:
             return -np.inf, np.inf
-        confidence_radius = np.sqrt(-np.log(self.confidence_level / 2) / (2 * n))
-        mean_reward = self.stage_rewards[stage]
-        return mean_reward - confidence_radius, mean_reward + confidence_radius
+        r = self._radius()[stage]
+        return self.stage_rewards[stage] - r, self.stage_rewards[stage] + r
 
     def should_explore(self, stage: int) -> bool:
-        if self.stage_counts[stage] < 10:
+        if self.stage_counts[stage] < self.MIN_PULLS:
             return True
-        upper_bounds = [self.get_confidence_bounds(i)[1] for i in range(4)]
-        return upper_bounds[stage] >= max(upper_bounds) - 0.1
+        upper = np.where(self.stage_counts > 0, self.stage_rewards + self._radius(), np.inf)
+        return bool(upper[stage] >= upper.max() - self.SLACK)
 
 
 class DynamicProgrammingSolver:

@@ -11,6 +11,7 @@
 namespace asd {
 
 static thread_local char g_err[512] = "";
+thread_local const Tuning* g_tuning = nullptr;
 static std::atomic<long long> g_launches{0};
 
 int set_error(const char* fmt, ...) {
@@ -101,6 +102,16 @@ int asd_stop_rule(const double* p, const double* C, int n, int L, double lam, in
                   double beta, int32_t* k_star, double* J, void* stream) {
     return launch_stop_rule(p, C, n, L, lam, risk_adjustment, alpha, beta, k_star, J,
                             static_cast<cudaStream_t>(stream));
+}
+int asd_stop_rule_rows(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
+                       double alpha, double beta, int32_t* k_star, double* J, void* stream) {
+    if (!lam) return set_error("asd_stop_rule_rows: lam is NULL");
+    return launch_stop_rule(p, C, n, L, 0.0, risk_adjustment, alpha, beta, k_star, J, static_cast<cudaStream_t>(stream),
+                            lam);
+}
+int asd_stop_rule_rows_host(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
+                            double alpha, double beta, int32_t* k_star, double* J) {
+    return stop_rule_rows_host(p, C, lam, n, L, risk_adjustment, alpha, beta, k_star, J);
 }
 int asd_stop_rule_host(const double* p, const double* C, int L, double lam, int risk_adjustment, double alpha,
                        double beta, double* J) {

@@ -479,18 +479,16 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     attn_stamp(a, 9);
 }
 
-int g_attn_wide = 0;
 unsigned long long* g_attn_trace = nullptr;
 int g_attn_trace_max = 0, g_attn_trace_next = 0;
 
 template <int HD, int KW, int NS>
 static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<HD, KW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
         prefer_max_smem(attn_mma_kernel<HD, KW, NS>);
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -501,7 +499,7 @@ static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cu
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cfg.attrs = attr;
-    cfg.numAttrs = g_glue_pdl ? 1 : 0;
+    cfg.numAttrs = tuning().glue_pdl ? 1 : 0;
     ASD_CUDA(cudaLaunchKernelEx(&cfg, attn_mma_kernel<HD, KW, NS>, a));
     return 0;
 }
@@ -523,7 +521,7 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     const int rg = (rows + 15) / 16;
     if (rg > 8) return set_error("attention: q_len * group = %d rows exceeds 128; chunk the query", rows);
     // key groups per row group: keep 4-8 warps per CTA so that one CTA per SM still hides latency
-    const int kg = g_attn_wide ? (rg <= 2 ? 4 : (rg <= 4 ? 2 : 1)) : (rg == 1 ? 4 : (rg == 2 ? 2 : 1));
+    const int kg = tuning().attn_wide ? (rg <= 2 ? 4 : (rg <= 4 ? 2 : 1)) : (rg == 1 ? 4 : (rg == 2 ? 2 : 1));
     const int warps = rg * kg;
     AttnArgs a;
     a.q = L.q;

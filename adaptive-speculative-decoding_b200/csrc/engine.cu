@@ -60,6 +60,8 @@ struct Engine {
     // options
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1, tp_two_shot = 0;
+    Tuning tune;   // per-engine knobs, installed for the calling thread by forward()
+    int device = 0;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
     // fused peer-memory all-reduce (CUDA IPC): double-buffered partials + flag array, local and peer views
@@ -138,11 +140,12 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
                    int n_logit_rows, float* logits_out, long long logits_ld, cudaStream_t s) {
     const asd_model_config& c = e->c;
     if (M <= 0) return 0;
+    TuningScope tuning_scope(&e->tune);
     if (M > c.max_tokens) return set_error("engine: M = %d exceeds max_tokens = %d", M, c.max_tokens);
     if (!e->embed || !e->kv_pool || !e->inv_freq) return set_error("engine: weights / KV pool not set");
     for (auto& L : e->layers)
         if (!L.wqkv) return set_error("engine: a layer has no weights");
-    const bool fn = e->fuse_norm != 0;   // RMSNorm folded into the consumer GEMMs (weights must be pre-folded)
+    const bool fn = e->fuse_norm != 0;   // RMSNorm fused into the GEMM epilogues (producer: bf16(resid * ln_w) + sum of squares; consumer: rstd)
     if (fn && !(e->reduce && e->fuse_rope)) return set_error("engine: fuse_norm needs reduce = 1 and fuse_rope = 1");
     Plans* P = nullptr;
     if (ensure_plans(e, M, &P)) return -1;
@@ -398,6 +401,7 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
     }
     Engine* e = new Engine();
     e->c = c;
+    cudaGetDevice(&e->device);
     e->nqkv = (c.n_heads + 2 * c.n_kv_heads) * c.head_dim;
     e->qdim = c.n_heads * c.head_dim;
     e->ffp = (c.ffn + 63) / 64 * 64;
@@ -554,12 +558,64 @@ int asd_engine_ipc_import(asd_engine_t* h, const void* all_handles) {
     return 0;
 }
 
+// In-process tensor parallelism: all ranks' engines live in ONE process on different devices (what
+// Stage(tensor_parallel_size = t, gpu_ids = [...]) builds).  With peer access enabled a cudaMalloc pointer of one
+// device is directly usable in kernels of the others (unified addressing), so no IPC handles are needed.
+int asd_engine_peer_connect(asd_engine_t** hs, int n) {
+    if (!hs || n < 1 || n > 8) return set_error("asd_engine_peer_connect: need 1..8 engines");
+    Engine* es[8];
+    for (int r = 0; r < n; ++r) {
+        es[r] = reinterpret_cast<Engine*>(hs[r]);
+        if (!es[r] || !es[r]->tp_buf[0] || es[r]->c.tp_size != n || es[r]->c.tp_rank != r)
+            return set_error("asd_engine_peer_connect: engine %d is not rank %d of a %d-way group", r, r, n);
+        for (int q = 0; q < r; ++q)
+            if (es[q]->device == es[r]->device)
+                return set_error("asd_engine_peer_connect: ranks %d and %d share device %d", q, r, es[r]->device);
+    }
+    int prev = 0;
+    ASD_CUDA(cudaGetDevice(&prev));
+    for (int r = 0; r < n; ++r) {
+        ASD_CUDA(cudaSetDevice(es[r]->device));
+        for (int q = 0; q < n; ++q) {
+            if (q == r) continue;
+            int can = 0;
+            ASD_CUDA(cudaDeviceCanAccessPeer(&can, es[r]->device, es[q]->device));
+            if (!can) {
+                cudaSetDevice(prev);
+                return set_error("asd_engine_peer_connect: device %d cannot access device %d", es[r]->device, es[q]->device);
+            }
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(es[q]->device, 0);
+            if (pe == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+            } else if (pe != cudaSuccess) {
+                cudaSetDevice(prev);
+                return set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", es[r]->device, es[q]->device,
+                                 cudaGetErrorString(pe));
+            }
+        }
+    }
+    ASD_CUDA(cudaSetDevice(prev));
+    for (int r = 0; r < n; ++r) {
+        for (int q = 0; q < n; ++q) {
+            es[r]->peer_buf[0][q] = es[q]->tp_buf[0];
+            es[r]->peer_buf[1][q] = es[q]->tp_buf[1];
+            es[r]->peer_flags[q] = es[q]->tp_flags;
+        }
+        es[r]->p2p = true;
+        es[r]->plans.clear();
+    }
+    return 0;
+}
+
 int asd_engine_tp_error(asd_engine_t* h) {
     Engine* e = reinterpret_cast<Engine*>(h);
     if (!e || !e->tp_error) return 0;
-    int v = 0;
-    if (cudaMemcpy(&v, e->tp_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return v;
+    int v = 0, prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != e->device) cudaSetDevice(e->device);
+    const cudaError_t rc = cudaMemcpy(&v, e->tp_error, sizeof(int), cudaMemcpyDeviceToHost);
+    if (prev != e->device) cudaSetDevice(prev);
+    return rc == cudaSuccess ? v : -1;
 }
 
 int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
@@ -573,13 +629,14 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "attn_target_ctas")) e->attn_target_ctas = value;
     else if (!strcmp(name, "attn_min_split_keys")) e->attn_min_split_keys = value < 64 ? 64 : value;
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
-    else if (!strcmp(name, "glue_pdl")) g_glue_pdl = value;
-    else if (!strcmp(name, "attn_wide")) g_attn_wide = value;
+    else if (!strcmp(name, "glue_pdl")) e->tune.glue_pdl = value;
+    else if (!strcmp(name, "attn_wide")) e->tune.attn_wide = value;
+    else if (!strcmp(name, "gemm_big")) e->tune.gemm_big = value;
     else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
-    else if (!strcmp(name, "early_trigger")) g_gemm_early_trigger = value;
-    else if (!strcmp(name, "headroom")) g_gemm_headroom = value;
-    else if (!strcmp(name, "recv_dedicated")) g_gemm_recv_dedicated = value;
-    else if (!strcmp(name, "next_prefetch_mb")) g_gemm_next_mb = value;
+    else if (!strcmp(name, "early_trigger")) e->tune.gemm_early_trigger = value;
+    else if (!strcmp(name, "headroom")) e->tune.gemm_headroom = value;
+    else if (!strcmp(name, "recv_dedicated")) e->tune.gemm_recv_dedicated = value;
+    else if (!strcmp(name, "next_prefetch_mb")) e->tune.gemm_next_mb = value;
     else if (!strcmp(name, "tp_fused")) e->tp_fused = value;
     else if (!strcmp(name, "tp_two_shot")) e->tp_two_shot = value;
     else if (!strcmp(name, "p2p")) e->p2p = value != 0 && e->peer_flags[0] != nullptr;
@@ -622,8 +679,24 @@ int asd_engine_forward(asd_engine_t* h, const int32_t* tokens, const int32_t* po
     if (!e) return set_error("asd_engine_forward: NULL handle");
     if (!tokens || !positions || !token_slot || !cu_q || !seq_slot || nseq <= 0 || max_qlen <= 0 || max_kv_len <= 0)
         return set_error("asd_engine_forward: bad argument");
-    return forward(e, tokens, positions, token_slot, M, cu_q, seq_slot, nseq, max_qlen, max_kv_len, logit_rows,
-                   n_logit_rows, logits_out, logits_ld, static_cast<cudaStream_t>(stream));
+    if ((long long)max_kv_len > (long long)e->max_pages * e->c.page_size)
+        return set_error("asd_engine_forward: max_kv_len = %d exceeds the page table (%d pages of %d positions)",
+                         max_kv_len, e->max_pages, e->c.page_size);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (e->c.tp_size > 1 && e->p2p) {
+        // the peer-memory all-reduce numbers its exchanges with a host-side epoch baked into the kernel arguments:
+        // a replayed graph would re-use stale epochs, so tensor-parallel forwards are not graph-capturable
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+            return set_error("asd_engine_forward: tensor-parallel forwards cannot be captured into a CUDA graph");
+    }
+    int prev = 0;
+    ASD_CUDA(cudaGetDevice(&prev));
+    if (prev != e->device) ASD_CUDA(cudaSetDevice(e->device));
+    const int rc = forward(e, tokens, positions, token_slot, M, cu_q, seq_slot, nseq, max_qlen, max_kv_len, logit_rows,
+                           n_logit_rows, logits_out, logits_ld, s);
+    if (prev != e->device) cudaSetDevice(prev);
+    return rc;
 }
 
 }  // extern "C"

@@ -656,18 +656,13 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
     return 0;
 }
 
-int g_gemm_early_trigger = 0;
-int g_gemm_headroom = 1;
-int g_gemm_recv_dedicated = 1;
 thread_local NextPrefetch g_gemm_next;   // set by the caller right before gemm_launch, consumed by it (per host thread)
-int g_gemm_next_mb = 0;          // L2 budget (MB) for the next kernel's weights (engine option "next_prefetch_mb"); off:
-                                 // measured neutral after the cluster barrier, -3..-6 % when issued before it
 unsigned long long* g_gemm_trace = nullptr;   // diagnostics buffer [max launches][kTraceCtas][kTraceSlots]
 int g_gemm_trace_max = 0, g_gemm_trace_next = 0;
 constexpr int kTraceCtas = 1024;   // the caller marked it (the GEMM that follows the latency-bound attention kernel)
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
-static int g_gemm_attr_set = 0;
+static PerDeviceOnce g_gemm_attr;
 
 static int device_props() {
     if (g_num_sms) return 0;
@@ -731,7 +726,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     // headroom: leave shared memory for that many CTAs of the NEXT kernel (programmatic launch + early trigger)
     // (measured: pays for the draft's 16-token tiles, whose rings stay >= 4 deep; costs the verify tiles a stage)
-    const int headroom = pl->MT <= 32 ? g_gemm_headroom : 0;
+    const int headroom = pl->MT <= 32 ? tuning().gemm_headroom : 0;
     const int budget = (225 * 1024) / (ctas_per_sm + headroom) - fixed - 1024;
     int stages = budget / stage_bytes;
     if (stages > 8) stages = 8;
@@ -743,7 +738,7 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
         if (ksplit > 8) return set_error("gemm: cluster reduction supports ksplit <= 8");
         const int cols_per = (pl->MT + ksplit - 1) / ksplit;
         const int recv = ksplit * cols_per * kTileN * 4;
-        if (pl->MT <= 32 && g_gemm_recv_dedicated) {
+        if (pl->MT <= 32 && tuning().gemm_recv_dedicated) {
             pl->recv_dedicated = 1;                     // small tiles: own receive buffer, one cluster barrier less
             recv_extra = recv + 16;
             while (stages > 2 && fixed + recv_extra + stages * stage_bytes > budget + fixed) --stages;
@@ -769,9 +764,9 @@ int gemm_plan(GemmPlan* pl, int M, int N, int K, int mode, int force_ksplit, int
 
 void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w) {
     g_gemm_next = NextPrefetch{};
-    if (g_gemm_next_mb <= 0 || next_w == nullptr || next.m_tiles != 1) return;
+    if (tuning().gemm_next_mb <= 0 || next_w == nullptr || next.m_tiles != 1) return;
     const long long ncta = (long long)next.n_tiles * next.ksplit;
-    int kp = (int)(((long long)g_gemm_next_mb << 20) / (ncta * kABytes));
+    int kp = (int)(((long long)tuning().gemm_next_mb << 20) / (ncta * kABytes));
     const int per_cta = (next.kblocks + next.ksplit - 1) / next.ksplit;
     if (kp > per_cta) kp = per_cta;
     if (kp <= 0) return;
@@ -785,11 +780,10 @@ void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w) {
 int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo,
                 int n_valid, bool pdl, cudaStream_t stream, bool accumulate, const QkvEpilogue* qkv,
                 const NormFusion* norm, const TpFusion* tp) {
-    if (!g_gemm_attr_set) {
+    if (g_gemm_attr.need()) {
         if (device_props()) return -1;
         ASD_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
         prefer_max_smem(gemm_ws_kernel);
-        g_gemm_attr_set = 1;
     }
     GemmArgs a;
     a.M = pl.M;
@@ -807,7 +801,7 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     a.reduce = pl.reduce;
     a.recv_dedicated = pl.recv_dedicated;
     a.accumulate = accumulate ? 1 : 0;
-    a.early_trigger = g_gemm_early_trigger;
+    a.early_trigger = tuning().gemm_early_trigger;
     a.norm = norm ? *norm : NormFusion{};
     a.tp = TpFusion{};
     a.next_ntiles = a.next_ksplit = a.next_kblocks = a.next_kp = 0;

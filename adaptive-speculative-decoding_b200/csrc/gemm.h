@@ -63,10 +63,8 @@ struct NextPrefetch {
     int ntiles = 0, ksplit = 1, kblocks = 0, kp = 0;
 };
 extern thread_local NextPrefetch g_gemm_next;
-extern int g_gemm_next_mb;
 // prefetch budget -> k-blocks per CTA of `next`; call right before launching the GEMM that precedes `next`
 void gemm_set_next(const GemmPlan& next, const CUtensorMap* next_w);
-extern int g_gemm_early_trigger, g_gemm_headroom, g_gemm_recv_dedicated;
 int gemm_token_tile(int M);
 // reduce = 1: the K splits of a tile form a thread-block cluster and reduce through DSMEM, so the fp32
 // output is final ([M][ldo], one slice) instead of one slice per split

@@ -16,7 +16,6 @@
 
 namespace asd {
 
-int g_glue_pdl = 1;   // launch the glue kernels programmatically (they wait on griddepcontrol)
 static void glue_carveout();   // same shared-memory carve-out for every glue kernel (see prefer_max_smem)
 
 constexpr int kNormThreads = 256;
@@ -121,7 +120,7 @@ int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_s
     cfg.blockDim = dim3(kNormThreads);
     cfg.stream = stream;
     cfg.attrs = attr;
-    cfg.numAttrs = g_glue_pdl ? 1 : 0;
+    cfg.numAttrs = tuning().glue_pdl ? 1 : 0;
     ASD_CUDA(cudaLaunchKernelEx(&cfg, add_norm_kernel, resid, part, nslices, slice_stride, tokens, emb, w, xnorm, h, eps,
                                 resid_bf, sumsq0));
     count_launch(1);
@@ -435,9 +434,8 @@ int launch_gather_rows(const __nv_bfloat16* src, const int* rows, __nv_bfloat16*
 }
 
 static void glue_carveout() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static PerDeviceOnce once;
+    if (!once.need()) return;
     prefer_max_smem(add_norm_kernel);
     prefer_max_smem(tp_allreduce_norm_kernel);
     prefer_max_smem(reduce_slices_kernel);

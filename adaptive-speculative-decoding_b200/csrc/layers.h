@@ -7,7 +7,6 @@
 
 namespace asd {
 
-extern int g_glue_pdl, g_attn_wide;
 
 int launch_add_norm(float* resid, const float* part, int nslices, size_t slice_stride, const int* tokens,
                     const __nv_bfloat16* emb, const __nv_bfloat16* w, __nv_bfloat16* xnorm, int M, int h, float eps,

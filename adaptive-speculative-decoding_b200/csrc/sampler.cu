@@ -802,9 +802,10 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int slot = ns ? kMaxSlabs + 1 + ns : num_slabs;   // cache index of (kernel, footprint)
-    if (g_max_clusters[slot] == 0) {
-        int dev = 0, optin = 0;
-        ASD_CUDA(cudaGetDevice(&dev));
+    static PerDeviceOnce attr_once[2 * kMaxSlabs + 16];   // the shared-memory opt-in is per (kernel, device)
+    int dev = 0;
+    if (attr_once[slot].need(&dev)) {
+        int optin = 0;
         ASD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         ASD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         cfg.gridDim = dim3(kCluster * 148);

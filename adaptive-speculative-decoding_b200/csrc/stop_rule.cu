@@ -78,22 +78,23 @@ __host__ __device__ __forceinline__ int stop_rule_one(const double* p_in, const 
 }
 
 __global__ void stop_rule_kernel(const double* __restrict__ p, const double* __restrict__ C, int n, int L, double lam,
-                                 int risk, double alpha, double beta, int* __restrict__ k_star,
-                                 double* __restrict__ J) {
+                                 const double* __restrict__ lam_rows, int risk, double alpha, double beta,
+                                 int* __restrict__ k_star, double* __restrict__ J) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     double Jl[kMaxStages + 1];
-    const int k = stop_rule_one<true>(p + (size_t)r * L, C + (size_t)r * L, L, lam, risk, alpha, beta, Jl);
+    const int k = stop_rule_one<true>(p + (size_t)r * L, C + (size_t)r * L, L, lam_rows ? lam_rows[r] : lam, risk,
+                                      alpha, beta, Jl);
     k_star[r] = k;
     for (int i = 0; i <= L; ++i) J[(size_t)r * (L + 1) + i] = Jl[i];
 }
 
 int launch_stop_rule(const double* p, const double* C, int n, int L, double lam, int risk_adjustment, double alpha,
-                     double beta, int* k_star, double* J, cudaStream_t stream) {
+                     double beta, int* k_star, double* J, cudaStream_t stream, const double* lam_rows) {
     if (L < 1 || L > kMaxStages) return set_error("asd_stop_rule: L must be in [1, %d]", kMaxStages);
     if (n <= 0) return 0;
     const int threads = 128, blocks = (n + threads - 1) / threads;
-    stop_rule_kernel<<<blocks, threads, 0, stream>>>(p, C, n, L, lam, risk_adjustment, alpha, beta, k_star, J);
+    stop_rule_kernel<<<blocks, threads, 0, stream>>>(p, C, n, L, lam, lam_rows, risk_adjustment, alpha, beta, k_star, J);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -103,6 +104,19 @@ int stop_rule_host(const double* p, const double* C, int L, double lam, int risk
                    double beta, double* J) {
     if (L < 1 || L > kMaxStages) return set_error("asd_stop_rule_host: L must be in [1, %d]", kMaxStages);
     return stop_rule_one<false>(p, C, L, lam, risk_adjustment, alpha, beta, J);
+}
+
+int stop_rule_rows_host(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
+                        double alpha, double beta, int* k_star, double* J) {
+    if (L < 1 || L > kMaxStages) return set_error("asd_stop_rule_rows_host: L must be in [1, %d]", kMaxStages);
+    if (!p || !C || !lam || !k_star) return set_error("asd_stop_rule_rows_host: NULL argument");
+    double Jl[kMaxStages + 1];
+    for (int r = 0; r < n; ++r) {
+        k_star[r] = stop_rule_one<false>(p + (size_t)r * L, C + (size_t)r * L, L, lam[r], risk_adjustment, alpha, beta, Jl);
+        if (J)
+            for (int i = 0; i <= L; ++i) J[(size_t)r * (L + 1) + i] = Jl[i];
+    }
+    return 0;
 }
 
 double bayesian_adjustment_host(double p_hat, double n_obs, double alpha, double beta) {

@@ -75,6 +75,12 @@ ASD_API int asd_reject_sample_host(const float* target_logits, const float* draf
  */
 ASD_API int asd_stop_rule(const double* p, const double* C, int n, int L, double lam, int risk_adjustment, double alpha,
                   double beta, int32_t* k_star, double* J, void* stream);
+/* same with one lambda per row (lam fp64 [n]): OptimalStoppingTable.precompute evaluates its whole
+ * lambda x probability grid with ONE call (src/algorithms/dp_solver.py:149-171 loops in Python) */
+ASD_API int asd_stop_rule_rows(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
+                       double alpha, double beta, int32_t* k_star, double* J, void* stream);
+ASD_API int asd_stop_rule_rows_host(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
+                            double alpha, double beta, int32_t* k_star, double* J);
 /* scalar host form used by the Python policy seam (pipeline.py:251-256): returns k_star or -1 */
 ASD_API int asd_stop_rule_host(const double* p, const double* C, int L, double lam, int risk_adjustment, double alpha,
                        double beta, double* J);
@@ -151,6 +157,11 @@ ASD_API int asd_engine_set_allreduce(asd_engine_t* e, void* comm, void* nccl_all
 ASD_API int asd_engine_ipc_export(asd_engine_t* e, void* handles_out);
 ASD_API int asd_engine_ipc_import(asd_engine_t* e, const void* all_handles);
 ASD_API int asd_engine_tp_error(asd_engine_t* e);
+/* In-process tensor parallelism (what Stage(tensor_parallel_size = t, gpu_ids = [...]) builds, mirroring
+ * configs/qwen3_models.yaml:10-51 and src/serving/real_model_pipeline.py:98-108): the t rank engines were created in
+ * ONE process, rank r on its own device.  Enables peer access between the devices and wires every rank's receive
+ * buffers and flags into the others (no IPC, no torchrun).  engines[r] must be rank r of a t-way group. */
+ASD_API int asd_engine_peer_connect(asd_engine_t** engines, int n);
 /* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
  * "reduce" (1 in-cluster split-K reduction with fused residual add, 0 fp32 slices summed by the glue
  * kernels), "fuse_rope" (1: bias + RoPE + q store + paged K/V append in the QKV GEMM epilogue),
@@ -188,7 +199,8 @@ ASD_API int asd_engine_profile_read(asd_engine_t* e, float* ms_by_class, int* la
  *   logit_rows i32 [n_logit_rows] selects rows (NULL = all M rows, n_logit_rows == M; 0 = no logits);
  *   logits_out fp32 [n_logit_rows, vocab] with row stride logits_ld elements (0 = vocab).
  * Asynchronous on `stream`; performs no allocation or synchronisation (CUDA-graph capturable after
- * one warm-up call with the same M).
+ * one warm-up call with the same M when tp_size == 1; a tensor-parallel forward numbers its peer-memory exchanges
+ * with a host-side epoch and refuses stream capture).  Runs on the device the engine was created on.
  */
 ASD_API int asd_engine_forward(asd_engine_t* e, const int32_t* tokens, const int32_t* positions,
                        const int32_t* token_slot, int M, const int32_t* cu_q, const int32_t* seq_slot, int nseq,

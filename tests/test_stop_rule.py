@@ -43,6 +43,62 @@ def test_table_and_solver_helpers():
     assert s.should_stop(0, 0.0, 0.05, 50.0) is False
 
 
+def test_rows_host_matches_scalar_rule():
+    rng = np.random.default_rng(3)
+    n, L = 257, 4
+    p, C, lam = rng.random((n, L)), rng.uniform(0.5, 12.0, (n, L)), rng.choice([0.1, 0.5, 1, 2, 5, 10], n)
+    for risk in (False, True):
+        k, J = dp_solver.stop_rule_rows(p, C, lam, risk, 2.0, 0.5)
+        for r in range(n):
+            k1, J1 = dp_solver.optimal_stopping_rule(list(p[r]), list(C[r]), float(lam[r]), risk, 2.0, 0.5)
+            assert k1 == k[r] and [x.hex() for x in J1] == [float(x).hex() for x in J[r]]
+
+
+def test_table_and_adaptive_match_live_reference():
+    """OptimalStoppingTable (one batched call) and AdaptiveStopping against the reference's own classes"""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    ref = ref_loader.dp_solver()
+    rng = np.random.default_rng(11)
+    lams = [0.1, 0.5, 1.0, 2.0, 5.0, 10.0]
+    grid = [[round(a, 2), round(b, 2), round(c, 2), 1.0] for a in np.linspace(0.05, 0.95, 7)
+            for b in np.linspace(0.1, 0.9, 5) for c in (0.3, 0.725, 0.9)]
+    grid += [[0.123, 0.456, 0.789, 1.0], [0.125, 0.455, 0.785, 1.0]]       # colliding rounded keys
+    costs = [1.0, 2.0, 4.5, 10.0]
+    mine, theirs = dp_solver.OptimalStoppingTable(lams), ref.OptimalStoppingTable(lams)
+    mine.precompute(costs, grid)
+    theirs.precompute(costs, grid)
+    assert mine.table == theirs.table
+    for _ in range(300):
+        pr = [round(float(x), int(rng.integers(2, 5))) for x in rng.random(4)]
+        lam = float(rng.uniform(0.05, 12.0))
+        for fb in (True, False):
+            assert mine.lookup(pr, lam, fb) == theirs.lookup(pr, lam, fb)
+    a, b = dp_solver.AdaptiveStopping(1.5, 0.05), ref.AdaptiveStopping(1.5, 0.05)
+    for _ in range(200):
+        st, q, lat = int(rng.integers(0, 4)), float(rng.random()), float(rng.uniform(50, 3000))
+        a.update_statistics(st, q, lat)
+        b.update_statistics(st, q, lat)
+        for s_ in range(4):
+            assert a.get_confidence_bounds(s_) == b.get_confidence_bounds(s_)
+            assert a.should_explore(s_) == b.should_explore(s_)
+    assert np.array_equal(a.stage_counts, b.stage_counts) and np.array_equal(a.stage_rewards, b.stage_rewards)
+    assert a.total_steps == b.total_steps
+
+
+@pytest.mark.gpu
+def test_device_rows_bit_exact():
+    import torch
+    rng = np.random.default_rng(5)
+    n, L = 5000, 3
+    p, C, lam = rng.random((n, L)), np.tile([1.0, 4.5, 10.0], (n, 1)), rng.choice([0.1, 0.5, 1, 2, 5, 10], n).astype(np.float64)
+    k_h, J_h = dp_solver.stop_rule_rows(p, C, lam)
+    k_d, J_d = dp_solver.stop_rule_rows(torch.from_numpy(p).cuda(), torch.from_numpy(C).cuda(), torch.from_numpy(lam).cuda())
+    assert np.array_equal(k_h, k_d.cpu().numpy())
+    assert np.array_equal(J_h.view(np.uint64), J_d.cpu().numpy().view(np.uint64))
+
+
 @pytest.mark.gpu
 def test_device_batch_bit_exact(stop_rule_golden):
     import torch
