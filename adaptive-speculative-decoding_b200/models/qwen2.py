@@ -63,9 +63,12 @@ def tiny_config(**kw) -> Qwen2Config:
 
 
 def random_hf_weights(cfg: Qwen2Config, seed: int, device="cpu", std: float = 0.02,
-                      dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+                      dtype=torch.bfloat16, logit_std: float = None) -> Dict[str, torch.Tensor]:
     """HF-named state dict with N(0, std^2) weights (norm weights 1 + N(0, std^2)), one seed per model
-    (SURVEY.md 8d synthetic inputs)."""
+    (SURVEY.md 8d synthetic inputs).  ``logit_std`` rescales the output embedding so that the logits have that
+    standard deviation (the final RMSNorm leaves unit-RMS activations, so logit std = head std * sqrt(hidden)):
+    the north-star tolerance "max-abs <= 2e-2" is an absolute bound stated for logits of ordinary magnitude,
+    and logit_std = 0.4 keeps |logit| < ~2 over a 152K vocabulary."""
     g = torch.Generator(device=device).manual_seed(seed)
     h, nh, nkv, hd, ff = (cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim,
                           cfg.intermediate_size)
@@ -91,6 +94,9 @@ def random_hf_weights(cfg: Qwen2Config, seed: int, device="cpu", std: float = 0.
     w["model.norm.weight"] = rn(h, mean=1.0)
     if not cfg.tie_word_embeddings:
         w["lm_head.weight"] = rn(cfg.vocab_size, h)
+    if logit_std is not None:
+        key = "model.embed_tokens.weight" if cfg.tie_word_embeddings else "lm_head.weight"
+        w[key] = (w[key].float() * (logit_std / (std * h ** 0.5))).to(dtype)
     return w
 
 
@@ -139,9 +145,11 @@ def pack_layer(w: Dict[str, torch.Tensor], cfg: Qwen2Config, l: int, tp_rank: in
     return out
 
 
-def random_packed_layer(cfg: Qwen2Config, gen: torch.Generator, tp_size: int = 1, device="cuda", std: float = 0.02):
+def random_packed_layer(cfg: Qwen2Config, gen: torch.Generator, tp_size: int = 1, device="cuda", std: float = 0.02,
+                        gen_replicated: torch.Generator = None):
     """Random weights generated directly in the engine layout (for the full-size benchmarks, where a
-    second HF-layout copy of 64-143 GB would not fit)."""
+    second HF-layout copy of 64-143 GB would not fit).  ``gen`` seeds the sharded matrices (one stream per
+    rank), ``gen_replicated`` the RMSNorm weights, which every rank must hold identically."""
     h, hd = cfg.hidden_size, cfg.head_dim
     nhl, nkvl, ffl = cfg.num_attention_heads // tp_size, cfg.num_key_value_heads // tp_size, cfg.intermediate_size // tp_size
     nqkv, ffp = (nhl + 2 * nkvl) * hd, (ffl + 63) // 64 * 64
@@ -152,5 +160,62 @@ def random_packed_layer(cfg: Qwen2Config, gen: torch.Generator, tp_size: int = 1
     wgu = rn(2 * ffp, h)
     if ffp != ffl:
         wgu.view(ffp // 64, 2, 64, h)[-1, :, ffl - (ffp - 64):, :] = 0
-    return {"wqkv": rn(nqkv, h), "bqkv": rn(nqkv), "wo": rn(h, nhl * hd), "wgateup": wgu, "wdown": rn(h, ffl),
-            "ln1": rn(h, mean=1.0), "ln2": rn(h, mean=1.0)}
+    out = {"wqkv": rn(nqkv, h), "bqkv": rn(nqkv), "wo": rn(h, nhl * hd), "wgateup": wgu, "wdown": rn(h, ffl)}
+    gr = gen_replicated if gen_replicated is not None else gen
+    for name in ("ln1", "ln2"):
+        out[name] = (torch.randn(h, generator=gr, device=device) * std + 1.0).to(torch.bfloat16)
+    return out
+
+
+def load_safetensors_dir(path: str) -> Dict[str, torch.Tensor]:
+    """HF checkpoint directory (``*.safetensors`` shards, as ``scripts/download_qwen3_models.py`` of the reference
+    stores them) -> HF-named state dict on the CPU.  Parsed directly (8-byte header length, JSON header, raw
+    little-endian tensors): the ``safetensors`` package is not a dependency."""
+    import glob
+    import json
+    import os
+    import struct
+
+    import numpy as np
+    files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors under {path}")
+    dtypes = {"BF16": (torch.bfloat16, 2), "F16": (torch.float16, 2), "F32": (torch.float32, 4)}
+    out: Dict[str, torch.Tensor] = {}
+    for fn in files:
+        with open(fn, "rb") as f:
+            (n,) = struct.unpack("<Q", f.read(8))
+            header = json.loads(f.read(n))
+        base = 8 + n
+        mm = np.memmap(fn, dtype=np.uint8, mode="r")
+        for name, meta in header.items():
+            if name == "__metadata__":
+                continue
+            if meta["dtype"] not in dtypes:
+                raise ValueError(f"{fn}: tensor {name} has unsupported dtype {meta['dtype']}")
+            dt, _ = dtypes[meta["dtype"]]
+            b, e = meta["data_offsets"]
+            raw = torch.from_numpy(np.array(mm[base + b:base + e]))       # copy out of the mapping
+            out[name] = raw.view(dt).reshape(meta["shape"])
+    return out
+
+
+def save_safetensors(w: Dict[str, torch.Tensor], filename: str) -> None:
+    """inverse of ``load_safetensors_dir`` for one shard (tests, tools)"""
+    import json
+    import struct
+    names = {torch.bfloat16: "BF16", torch.float16: "F16", torch.float32: "F32"}
+    header, blobs, off = {}, [], 0
+    for k, t in w.items():
+        t = t.contiguous().cpu()
+        raw = t.view(torch.uint8).numpy().tobytes() if t.numel() else b""
+        header[k] = {"dtype": names[t.dtype], "shape": list(t.shape), "data_offsets": [off, off + len(raw)]}
+        blobs.append(raw)
+        off += len(raw)
+    hb = json.dumps(header).encode()
+    hb += b" " * (-len(hb) % 8)
+    with open(filename, "wb") as f:
+        f.write(struct.pack("<Q", len(hb)))
+        f.write(hb)
+        for b in blobs:
+            f.write(b)

@@ -87,83 +87,168 @@ def load_tokenizer(model_name: str, vocab_size: int):
 
 @dataclass
 class StageConfig:
-    """server.py:151-158"""
+    """server.py:151-158 (+ ``gpu_ids`` / ``max_model_len`` of configs/qwen3_models.yaml:10-51)"""
     model_name: str
     model_size: str
     tensor_parallel_size: int = 1
     gpu_memory_utilization: float = 0.8
     quantized: bool = False
     cost_per_token: Optional[float] = None
+    gpu_ids: Optional[List[int]] = None
+    max_model_len: Optional[int] = None
+    config: Optional[Qwen2Config] = None      # architecture override (e.g. a layer-truncated shape for tests)
+
+
+def validate_gpu_assignment(stages) -> None:
+    """The reference's placement rules (src/config/model_config.py:136-150): a stage needs exactly
+    ``tensor_parallel_size`` GPUs and no GPU may serve two stages.  ``stages``: iterable of
+    (label, tensor_parallel_size, gpu_ids)."""
+    seen = {}
+    for label, tp, gpus in stages:
+        if len(gpus) != tp:
+            raise ModelLoadError(f"Stage {label}: GPU count ({len(gpus)}) doesn't match tensor_parallel_size ({tp})")
+        if len(set(gpus)) != len(gpus):
+            raise ModelLoadError(f"Stage {label}: duplicate GPU ids {gpus}")
+        for g in gpus:
+            if g in seen:
+                raise ModelLoadError(f"GPU IDs cannot be assigned to multiple stages (GPU {g}: {seen[g]} and {label})")
+            seen[g] = label
+
+
+_ORDER = threading.Lock()
+_NEXT_ORDER = [0]
 
 
 class Stage:
     """One model of the cascade.  ``generate`` keeps the reference's contract:
-    ``(texts, logprobs, stats)`` with ``stats["generation_time_ms"]`` (pipeline.py:204-209,245)."""
+    ``(texts, logprobs, stats)`` with ``stats["generation_time_ms"]`` (pipeline.py:204-209,245).
+
+    ``tensor_parallel_size = t`` shards the model Megatron-style over ``gpu_ids`` (t GPUs of this process,
+    exchanging partial sums over NVLink peer memory) exactly where the reference passes ``tensor_parallel_size``
+    to ``vllm.LLM`` (RESEARCH_PROTOCOL.md:262-268, real_model_pipeline.py:98-108).  ``draft`` is the previous
+    (smaller) stage whose engine proposes k tokens per step; it may sit on another GPU."""
 
     def __init__(self, model_name: str, model_size: str, tensor_parallel_size: int = 1,
                  gpu_memory_utilization: float = 0.8, quantized: bool = False, *,
                  cost_per_token: Optional[float] = None, config: Optional[Qwen2Config] = None,
                  draft: Optional["Stage"] = None, k: int = 5, weights: Optional[dict] = None, seed: int = 0,
-                 max_batch: int = 16, max_model_len: int = 4096, device="cuda", gpu_ids: Optional[List[int]] = None):
+                 max_batch: int = 16, max_model_len: int = 4096, device=None, gpu_ids: Optional[List[int]] = None,
+                 allow_random_weights: bool = True):
         self.model_name, self.model_size = model_name, model_size.lower()
-        self.tensor_parallel_size = tensor_parallel_size
+        self.tensor_parallel_size = int(tensor_parallel_size)
         self.gpu_memory_utilization, self.quantized = gpu_memory_utilization, quantized
         if quantized:
             logger.warning("quantized=True is ignored: the B200 engine runs bf16 weights")
-        if tensor_parallel_size != 1:
-            raise ModelLoadError("in-process Stage supports tensor_parallel_size == 1; tensor-parallel targets "
-                                 "are launched one process per GPU (asd_b200.parallel, bench.py --gpus N)")
+        if self.tensor_parallel_size < 1:
+            raise ModelLoadError("tensor_parallel_size must be >= 1")
+        if gpu_ids is None:
+            if device is not None:
+                import torch
+                d = torch.device(device)
+                first = d.index if d.index is not None else 0
+            else:
+                first = 0
+            gpu_ids = list(range(first, first + self.tensor_parallel_size))
+        self.gpu_ids = [int(g) for g in gpu_ids]
+        validate_gpu_assignment([(self.model_size, self.tensor_parallel_size, self.gpu_ids)])
         try:
             self.cfg = config or get_config(self.model_size)
         except KeyError as e:
             raise ModelLoadError(f"unknown model size {model_size!r}") from e
+        if self.cfg.num_key_value_heads % self.tensor_parallel_size or self.cfg.intermediate_size % self.tensor_parallel_size:
+            raise ModelLoadError(f"{self.model_size}: {self.cfg.num_key_value_heads} KV heads / ffn "
+                                 f"{self.cfg.intermediate_size} do not split over {self.tensor_parallel_size} ranks")
         self.cost_per_token = cost_per_token if cost_per_token is not None else COST_PER_TOKEN.get(self.model_size, 1.0)
         self.draft, self.k = draft, k
         self.max_batch, self.max_model_len = max_batch, max_model_len
         self.tokenizer = load_tokenizer(model_name, self.cfg.vocab_size)
-        self._lock = threading.Lock()       # the pipeline calls generate() from up to 100 threads
+        self._lock = threading.RLock()       # the pipeline calls generate() from up to 100 threads
+        with _ORDER:
+            self._order = _NEXT_ORDER[0]
+            _NEXT_ORDER[0] += 1
         try:
-            from ..engine import QwenEngine
-            self.engine = QwenEngine(self.cfg, max_seqs=max_batch, max_seq_len=max_model_len,
-                                     max_tokens=max(256, max_batch * (k + 1)), device=device)
-            if weights is not None:
-                self.engine.load_hf_weights(weights)
+            import torch
+            if not torch.cuda.is_available():
+                raise ModelLoadError("Stage needs CUDA devices (the engine has no CPU fallback)")
+            if max(self.gpu_ids) >= torch.cuda.device_count():
+                raise ModelLoadError(f"Stage {self.model_size}: gpu_ids {self.gpu_ids} but only "
+                                     f"{torch.cuda.device_count()} CUDA devices are visible")
+            from ..engine import QwenEngine, TPQwenEngine
+            mt = max(256, max_batch * (k + 1))
+            if self.tensor_parallel_size == 1:
+                self.engine = QwenEngine(self.cfg, max_seqs=max_batch, max_seq_len=max_model_len, max_tokens=mt,
+                                         device=f"cuda:{self.gpu_ids[0]}")
             else:
-                self.engine.load_random(seed)
+                self.engine = TPQwenEngine(self.cfg, self.gpu_ids, max_seqs=max_batch, max_seq_len=max_model_len,
+                                           max_tokens=mt)
+            self.weights_source = self._load_weights(weights, seed, allow_random_weights)
         except AsdError:
             raise
         except Exception as e:
             raise ModelLoadError(f"failed to load {model_name}: {e}") from e
 
+    def _load_weights(self, weights, seed, allow_random):
+        import os
+        if weights is not None:
+            self.engine.load_hf_weights(weights)
+            return "state_dict"
+        if os.path.isdir(self.model_name):
+            from .qwen2 import load_safetensors_dir
+            try:
+                w = load_safetensors_dir(self.model_name)
+            except FileNotFoundError:
+                w = None
+            if w is not None:
+                self.engine.load_hf_weights(w)
+                return "safetensors:" + self.model_name
+        if not allow_random:
+            raise ModelLoadError(f"no checkpoint found at {self.model_name!r} and random weights are not allowed")
+        logger.warning("Stage %s: no checkpoint at %r - running RANDOM-INIT weights of the %s shape (seed %d); "
+                       "outputs are meaningless text, timings are real", self.model_size, self.model_name,
+                       self.cfg.name, seed)
+        self.engine.load_random(seed)
+        return f"random(seed={seed})"
+
     # ------------------------------------------------------------------ reference API
     def generate(self, prompts: List[str], max_tokens: int = 512, temperature: float = 0.7, top_p: float = 0.9,
                  return_logprobs: bool = True) -> Tuple[List[str], List[np.ndarray], Dict[str, float]]:
-        """top_p is accepted for signature compatibility; sampling is over the full softmax(z/T)."""
+        """Prompts of any lengths are decoded together (ragged prefill, one batch of up to ``max_batch``).
+        ``top_p`` is accepted for signature compatibility (RESEARCH_PROTOCOL.md:272-279); sampling is over
+        the full softmax(z / T) - values below 1.0 are logged once and not applied."""
+        if top_p is not None and top_p < 1.0 and not getattr(self, "_top_p_warned", False):
+            self._top_p_warned = True
+            logger.info("top_p=%.2f is not applied: the fused sampler draws from the full softmax(z/T)", top_p)
         t0 = time.time()
         ids = [self._encode(p) for p in prompts]
         texts: List[Optional[str]] = [None] * len(prompts)
         lps: List[Optional[np.ndarray]] = [None] * len(prompts)
         acc_tok = steps = 0
-        with self._lock:
-            by_len: Dict[int, List[int]] = {}
-            for i, x in enumerate(ids):
-                by_len.setdefault(len(x), []).append(i)
-            for _, idx in by_len.items():
-                for s in range(0, len(idx), self.max_batch):
-                    grp = idx[s:s + self.max_batch]
-                    toks, lp, fused, st = self._generate_ids([ids[i] for i in grp], max_tokens, temperature)
-                    acc_tok += st["accepted"]
-                    steps += st["steps"]
-                    for j, i in enumerate(grp):
-                        texts[i] = self.tokenizer.decode(toks[j])
-                        lps[i] = make_logprobs(lp[j], fused[j]) if return_logprobs else np.array([])
+        # a stage's engine also serves as the NEXT stage's draft: whole generations are serialised per engine,
+        # locks taken in creation order (smaller stage first) so two stages can never deadlock
+        chain = sorted([st for st in (self.draft, self) if st is not None], key=lambda st: st._order)
+        for st in chain:
+            st._lock.acquire()
+        try:
+            order = sorted(range(len(ids)), key=lambda i: len(ids[i]))      # similar lengths share a batch
+            for s in range(0, len(order), self.max_batch):
+                grp = order[s:s + self.max_batch]
+                toks, lp, fused, st = self._generate_ids([ids[i] for i in grp], max_tokens, temperature)
+                acc_tok += st["accepted"]
+                steps += st["steps"]
+                for j, i in enumerate(grp):
+                    texts[i] = self.tokenizer.decode(toks[j])
+                    lps[i] = make_logprobs(lp[j], fused[j]) if return_logprobs else np.array([])
+        finally:
+            for st in reversed(chain):
+                st._lock.release()
         stats = {"generation_time_ms": (time.time() - t0) * 1000.0, "draft_tokens_accepted": acc_tok,
                  "decode_steps": steps}
         return texts, lps, stats
 
     def get_model_info(self) -> Dict[str, object]:
         return {"model_name": self.model_name, "model_size": self.model_size, "parameters": self.cfg.params,
-                "tensor_parallel_size": self.tensor_parallel_size, "cost_per_token": self.cost_per_token,
+                "tensor_parallel_size": self.tensor_parallel_size, "gpu_ids": list(self.gpu_ids),
+                "cost_per_token": self.cost_per_token, "weights": self.weights_source,
                 "dtype": "bfloat16", "hidden_size": self.cfg.hidden_size, "num_layers": self.cfg.num_hidden_layers,
                 "draft": None if self.draft is None else self.draft.model_size, "engine": "asd_b200 (sm_100a)"}
 
@@ -180,34 +265,34 @@ class Stage:
         ids = list(enc(text))
         return ids[-(self.max_model_len // 2):] or [0]
 
+    def _draft_engine(self):
+        d = self.draft
+        if d is None:
+            return None
+        if d.cfg.vocab_size != self.cfg.vocab_size:
+            if not getattr(self, "_vocab_warned", False):
+                self._vocab_warned = True
+                logger.warning("stage %s cannot draft for %s (vocabularies differ): plain decoding", d.model_size,
+                               self.model_size)
+            return None
+        return d.engine
+
     def _generate_ids(self, prompts: List[List[int]], max_tokens: int, temperature: float):
-        import torch
         from ..engine import SpecDecoder
-        B, P = len(prompts), len(prompts[0])
-        max_new = max(1, min(max_tokens, self.max_model_len - P - self.k - 2))
-        dec = SpecDecoder(self.engine, None if self.draft is None else self.draft.engine, B, self.k, temperature)
+        B, P = len(prompts), max(len(p) for p in prompts)
+        draft = self._draft_engine()
+        max_len = self.max_model_len if draft is None else min(self.max_model_len, self.draft.max_model_len)
+        max_new = max(1, min(max_tokens, max_len - P - self.k - 2))
         try:
-            first = dec.prefill(torch.tensor(prompts, dtype=torch.int32))
+            dec = SpecDecoder(self.engine, draft, B, self.k, temperature)
+            toks, lp, fused, st = dec.generate(prompts, max_new)
+        except InferenceError:
+            raise
         except AsdError as e:
             raise InferenceError(str(e)) from e
-        toks = [[int(t)] for t in first.cpu().tolist()]
-        lp = [[0.0] for _ in range(B)]
-        fused = [[np.zeros(6, np.float32)] for _ in range(B)]
-        accepted = steps = 0
-        while min(len(t) for t in toks) < max_new:
-            out = dec.step()
-            steps += 1
-            ot, n = out["out_tokens"].cpu().numpy(), out["accepted_len"].cpu().numpy()
-            ol, of = out["out_logprobs"].cpu().numpy(), out["features"].cpu().numpy()
-            accepted += int(n.sum())
-            for b in range(B):
-                m = int(n[b]) + 1
-                toks[b] += [int(x) for x in ot[b, :m]]
-                lp[b] += [float(x) for x in ol[b, :m]]
-                fused[b] += [of[b, i] for i in range(m)]
-        toks = [t[:max_new] for t in toks]
-        return (toks, [np.asarray(x[:max_new]) for x in lp], [np.stack(f[:max_new]) for f in fused],
-                {"accepted": accepted, "steps": steps})
+        toks, lp, fused = toks.numpy(), lp.numpy().astype(np.float64), fused.numpy()
+        return ([[int(x) for x in toks[b]] for b in range(B)], [lp[b] for b in range(B)],
+                [fused[b] for b in range(B)], st)
 
 
 class StageManager:
@@ -218,16 +303,31 @@ class StageManager:
 
     def __init__(self, stage_configs: List[StageConfig], gpu_allocation: Optional[Dict[str, List[int]]] = None, *,
                  speculative: bool = True, k: int = 5, stage_kwargs: Optional[dict] = None):
-        self.gpu_allocation = gpu_allocation or {}
+        self.gpu_allocation = {str(k_).lower(): list(v) for k_, v in (gpu_allocation or {}).items()}
         self.stages: Dict[str, Stage] = {}
         self.order: List[str] = []
         prev: Optional[Stage] = None
-        for i, sc in enumerate(stage_configs):
-            gpus = self.gpu_allocation.get(sc.model_size, [0])
+        placement, nxt = [], 0
+        for sc in stage_configs:
+            gpus = self.gpu_allocation.get(sc.model_size.lower(), sc.gpu_ids)
+            if gpus is None:
+                # no explicit placement: single-GPU stages share GPU 0 (one box, one GPU), sharded stages take
+                # the next free block
+                gpus = [0] if sc.tensor_parallel_size == 1 else list(range(nxt, nxt + sc.tensor_parallel_size))
+            nxt = max(nxt, max(gpus) + 1)
+            placement.append(list(gpus))
+        explicit = [(sc.model_size, sc.tensor_parallel_size, g) for sc, g in zip(stage_configs, placement)
+                    if self.gpu_allocation.get(sc.model_size.lower(), sc.gpu_ids) is not None]
+        validate_gpu_assignment(explicit)            # model_config.py:136-150
+        for i, (sc, gpus) in enumerate(zip(stage_configs, placement)):
             kw = dict(stage_kwargs or {})
+            if sc.max_model_len is not None:
+                kw.setdefault("max_model_len", sc.max_model_len)
+            if sc.config is not None:
+                kw["config"] = sc.config
             st = Stage(sc.model_name, sc.model_size, sc.tensor_parallel_size, sc.gpu_memory_utilization, sc.quantized,
                        cost_per_token=sc.cost_per_token, draft=prev if speculative else None, k=k, seed=i,
-                       device=f"cuda:{gpus[0]}" if gpus else "cuda", gpu_ids=gpus, **kw)
+                       gpu_ids=gpus, **kw)
             key = sc.model_size.lower()
             self.stages[key] = st
             self.order.append(key)

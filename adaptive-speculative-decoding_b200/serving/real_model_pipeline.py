@@ -101,7 +101,7 @@ class RealModelStage:
         self.model = Stage(self.config.model_path, _size_from_name(self.config.name),
                            tensor_parallel_size=self.config.tensor_parallel_size, draft=draft,
                            max_model_len=self.config.max_model_len,
-                           device=f"cuda:{self.config.gpu_ids[0]}" if self.config.gpu_ids else "cuda", **self._kw)
+                           gpu_ids=list(self.config.gpu_ids) if self.config.gpu_ids else None, **self._kw)
         self.is_loaded = True
 
     def unload_model(self):
@@ -134,6 +134,10 @@ class RealModelPipeline:
     def __init__(self, stage_configs: List[StageConfig], lambda_param: float = 1.0, speculative: bool = True,
                  predictor: Optional[QualityPredictor] = None, stage_kwargs: Optional[dict] = None):
         self.stages: List[RealModelStage] = []
+        if any(sc.tensor_parallel_size > 1 for sc in stage_configs):
+            # sharded stages own their GPUs: the reference's placement rules apply (src/config/model_config.py:136-150)
+            from ..models.stage import validate_gpu_assignment
+            validate_gpu_assignment([(sc.name, sc.tensor_parallel_size, list(sc.gpu_ids)) for sc in stage_configs])
         for i, sc in enumerate(stage_configs):
             self.stages.append(RealModelStage(sc, i, self.stages[-1] if (speculative and self.stages) else None,
                                               stage_kwargs))

@@ -179,15 +179,34 @@ def create_app_from_config(config: Dict[str, Any]) -> FastAPI:
                                cleanup_interval=cache_cfg.get("cache_cleanup_interval", 300))
     stage_cfgs, alloc = [], {}
     for st in config.get("models", {}).get("stages", []):
-        stage_cfgs.append(StageConfig(st["model_name"], st["size"], st.get("tensor_parallel_size", 1),
-                                      st.get("gpu_memory_utilization", 0.8), st.get("quantized", False),
-                                      st.get("cost_per_token", 1.0)))
-        alloc[st["size"]] = st.get("gpu_ids", [0])
-    manager = StageManager(stage_cfgs, alloc)
-    predictor = QualityPredictor(feature_dim=config.get("predictor", {}).get("feature_dim", 256))
+        q = st.get("quantized", st.get("quantization", False))
+        if isinstance(q, dict):
+            q = bool(q.get("enabled", False))
+        stage_cfgs.append(StageConfig(st.get("model_name", st.get("model_path", st.get("name", ""))),
+                                      st.get("size", st.get("size_label")), int(st.get("tensor_parallel_size", 1)),
+                                      st.get("gpu_memory_utilization", st.get("gpu_memory_fraction", 0.8)), bool(q),
+                                      st.get("cost_per_token", 1.0), max_model_len=st.get("max_model_len")))
+        if st.get("gpu_ids") is not None:
+            alloc[stage_cfgs[-1].model_size] = list(st["gpu_ids"])
+    manager = StageManager(stage_cfgs, alloc, stage_kwargs=config.get("engine", {}).get("stage_kwargs"))
+    pred_cfg = config.get("predictor", {})
+    predictor = QualityPredictor(feature_dim=pred_cfg.get("feature_dim", 256))
+    ckpt = pred_cfg.get("checkpoint", "checkpoints/predictor.pt")         # server.py:170-176
+    if ckpt and os.path.exists(ckpt):
+        predictor.load_model(ckpt)
+        logger.info(f"Loaded predictor from {ckpt}")
+    else:
+        logger.warning(f"Predictor weights not found at {ckpt}, using random weights")
+    risk = pcfg.get("risk_adjustment", {})                                # server.py:183-193
+    if isinstance(risk, dict):
+        risk_on, risk_a, risk_b = bool(risk.get("enabled", True)), float(risk.get("alpha", 1.0)), float(risk.get("beta", 1.0))
+    else:
+        risk_on, risk_a, risk_b = bool(risk), float(pcfg.get("risk_alpha", 1.0)), float(pcfg.get("risk_beta", 1.0))
     pipe = AdaptiveSpeculativePipeline(
         manager, predictor, FeatureExtractor(),
-        PipelineConfig(lambda_value=pcfg.get("lambda_value", 1.0), risk_adjustment=pcfg.get("risk_adjustment", False)),
+        PipelineConfig(lambda_value=pcfg.get("lambda_value", 1.0), risk_adjustment=risk_on, risk_alpha=risk_a,
+                       risk_beta=risk_b, enable_caching=cache_cfg.get("enable_kv_cache", True),
+                       max_concurrent_requests=config.get("safety", {}).get("max_concurrent_requests", 100)),
         cache_manager=cache)
     if pcfg.get("warmup", True):
         pipe.warmup()

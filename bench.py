@@ -87,6 +87,11 @@ def config_dict(wl, n_gpus, extra=None):
 
 # ------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """CPU arm.  The line's ``value`` is the same metric on the same config as our arm (configs[2]); a full
+    7B -> 32B step on CPU takes minutes, so it is a bounded sample multiplied out (``"extrapolated": true``).
+    Next to it ``cpu_baselines`` holds three MEASURED, un-extrapolated baselines: the stop
+    rule over 10^5 triples in CPython, the C sampler oracle on two config-2 grid points, and configs[0] end to end
+    (HF Qwen2ForCausalLM fp32, 0.5B -> 1.5B, k = 4, greedy) - our arm reports the same three on the GPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -95,21 +100,270 @@ def run_reference(args):
     wl = workload(args)
     oracle.build()
     cores = os.cpu_count()
-    vals = []
-    for _ in range(2 if args.steps > 1 else 1):
-        r = spec_step_baseline(wl["target"], wl["draft"], wl["B"], wl["k"], wl["prefix"], wl["T"], sample_layers=1,
-                               threads=cores)
-        vals.append(r)
-    r = min(vals, key=lambda x: x["step_seconds"])
+    t_start = time.time()
+    r = spec_step_baseline(wl["target"], wl["draft"], wl["B"], wl["k"], wl["prefix"], wl["T"], sample_layers=1,
+                           threads=cores)
     value = r["tokens_per_step"] / r["step_seconds"]
+    measured = {}
+    if not args.no_cpu_baseline:
+        measured = measured_cpu_baselines(cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["step_seconds"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32 (bf16-valued weights)",
-            "data": "synthetic", "config": config_dict(wl, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": r["sample"]},
+            "data": "synthetic", "config": config_dict(wl, args.gpus), "extrapolated": True,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": r["sample"],
+                             "extrapolated": True},
+            "cpu_baselines": measured, "wall_seconds": round(time.time() - t_start, 1),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def measured_cpu_baselines(cores):
+    """the three measured CPU baselines (each runs to completion inside this call; nothing multiplied out)"""
+    import numpy as np
+    import oracle
+    from oracle import config1_cpu, stop_rule_py
+    from asd_b200.models.qwen2 import QWEN25
+    out = {"stop_rule": stop_rule_py.time_triples(100_000, seed=7)}
+    grid = []
+    for B, k in ((16, 5), (64, 8)):
+        rng = np.random.default_rng(4321)
+        V, T = 152064, 0.7
+        tl = (rng.standard_normal((B, k + 1, V), dtype=np.float32) * 2)
+        dl = (tl[:, :k] + rng.standard_normal((B, k, V), dtype=np.float32))
+        dt = dl.argmax(-1).astype(np.int32)
+        t0 = time.perf_counter()
+        oracle.reject_sample(tl, dl, dt, rng.random((B, k)), rng.random(B), T)
+        dtm = time.perf_counter() - t0
+        grid.append({"B": B, "k": k, "V": V, "seconds": dtm, "rows_per_second": B * (k + 1) / dtm,
+                     "GB_per_s": (B * k * 2 * V * 4 + B * V * 4) / dtm / 1e9})
+    out["sampler"] = {"kind": "port", "cores": 1, "what": "oracle/sampler_oracle.c (scalar C), fixed uniforms, T = 0.7",
+                      "grid": grid}
+    out["config1"] = dict(config1_cpu.run(QWEN25["0.5b"], QWEN25["1.5b"], k=4, prompt_len=64, steps=8, threads=cores),
+                          kind="reference-stack (HF transformers, the model code the reference's data generation calls)")
+    return out
+
+
+def load_traffic():
+    """DRAM bytes actually moved per algorithmic byte for the dominant kernel, from the committed ncu capture
+    (profiles/traffic.json, written by tools/ncu_summary.py from `ncu --set full`); None if there is no capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
+def tp_check(torch, dist, rank, world, dev, dec, target, tcfg):
+    """Driver-visible tensor-parallel parity (runs after the timed region, N > 1):
+    1. every rank's verify logits of the last timed step must be bit-identical (ranks stay in lock step without
+       exchanging tokens only if they are), 2. no rank may have timed out waiting for a peer
+       (asd_engine_tp_error), 3. a 2-layer model of the target's width is run on M = 96 tokens by the N-way sharded
+       engine and by a single-GPU engine on rank 0; their logits must agree far inside the bf16 tolerance."""
+    from dataclasses import replace
+    from asd_b200.engine import QwenEngine
+    from asd_b200.models.qwen2 import random_hf_weights
+    lg = dec.target_logits
+    chk = torch.stack([lg.double().sum(), lg.double().abs().sum(), lg.view(-1)[::4099].double().square().sum(),
+                       lg.argmax(-1).double().sum()])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    identical = all(torch.equal(allc[0], c) for c in allc)
+    err = torch.tensor([float(target.tp_error())], device=dev)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    cfg2 = replace(tcfg, num_hidden_layers=2)
+    w = random_hf_weights(cfg2, seed=3, device=dev, logit_std=0.4)      # same seed, same device type: same weights on all ranks
+    B, q = 16, 6
+    ids = torch.randint(0, cfg2.vocab_size, (B, q), generator=torch.Generator().manual_seed(7)).to(dev).to(torch.int32)
+    slots = torch.arange(B, dtype=torch.int32, device=dev)
+    zero = torch.zeros(B, dtype=torch.int32, device=dev)
+    sh = QwenEngine(cfg2, max_seqs=B, max_seq_len=64, max_tokens=256, tp_rank=rank, tp_size=world, device=dev)
+    sh.load_hf_weights(w)
+    sh.enable_p2p()
+    got = sh.forward_uniform(ids, zero, slots, q)
+    torch.cuda.synchronize()
+    dist.barrier()
+    err2 = torch.tensor([float(sh.tp_error())], device=dev)
+    dist.all_reduce(err2, op=dist.ReduceOp.MAX)
+    max_abs = None
+    if rank == 0:
+        one = QwenEngine(cfg2, max_seqs=B, max_seq_len=64, max_tokens=256, device=dev).load_hf_weights(w)
+        ref = one.forward_uniform(ids, zero, slots, q)
+        torch.cuda.synchronize()
+        max_abs = float((got - ref).abs().max())
+        agree = float((got.argmax(-1) == ref.argmax(-1)).float().mean())
+        one.close()
+    sh.close()
+    del w
+    torch.cuda.empty_cache()
+    out = {"ranks_identical": bool(identical), "tp_error": int(max(err.item(), err2.item()))}
+    if rank == 0:
+        out.update(max_abs_vs_tp1_sample=max_abs, argmax_agree_vs_tp1_sample=agree,
+                   sample=f"2 layers of {tcfg.name} at M={B * q}, sharded x{world} vs one GPU")
+        out["ok"] = bool(identical and out["tp_error"] == 0 and max_abs <= 5e-3)
+    return out
+
+
+def config5(torch, dist, rank, world, dev, args, peaks):
+    """BASELINE configs[4]: Qwen2.5-72B verify-only at TP = N, batch 64, 4096-token prefix, k = 8 (576 tokens per
+    forward), paged KV.  The KV prefix is N(0,1) bf16 written straight into the paged pool (SURVEY 8d allows it
+    for the verify-only sweep: a real 64 x 4096-token prefill is 38 PFLOP); everything timed is the real forward."""
+    from asd_b200.engine import QwenEngine
+    from asd_b200.models.qwen2 import QWEN25
+    cfg = QWEN25["72b"]
+    B, k, prefix = 64, 8, 4096
+    M = B * (k + 1)
+    eng = QwenEngine(cfg, max_seqs=B, max_seq_len=prefix + 64, max_tokens=M, tp_rank=rank, tp_size=world, device=dev)
+    eng.load_random(seed=2)
+    eng.enable_p2p()
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    pool = eng.kv_pool
+    step = 1 << 28
+    for o in range(0, pool.numel(), step):
+        pool[o:o + step].normal_(generator=g)
+    toks = torch.randint(0, cfg.vocab_size, (B, k + 1), generator=torch.Generator().manual_seed(5)).to(dev).to(torch.int32)
+    slots = torch.arange(B, dtype=torch.int32, device=dev)
+    start = torch.full((B,), prefix, dtype=torch.int32, device=dev)
+    logits = torch.empty(M, cfg.vocab_size, dtype=torch.float32, device=dev)
+    run = lambda: eng.forward_uniform(toks, start, slots, prefix + k + 1, logits_out=logits)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    dist.barrier()
+    n = 8
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(n):
+        run()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1]) / n], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    eng.set_option("profile", 1)
+    run()
+    prof = eng.profile_read()
+    eng.set_option("profile", 0)
+    tp_err = eng.tp_error()
+    dist.barrier()
+    eng.close()
+    del eng, pool, logits
+    torch.cuda.empty_cache()
+    ms = float(ms.item())
+    params = cfg.streamed_bytes() / 2
+    gemm_flops = 2.0 * M * params / world
+    attn_flops = 4.0 * M * (prefix + k + 1) * cfg.num_attention_heads * cfg.head_dim * cfg.num_hidden_layers / world
+    tensor_floor_ms = (gemm_flops + attn_flops) / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3
+    kv_bytes = B * prefix * cfg.kv_bytes_per_token() / world
+    hbm_floor_ms = (cfg.streamed_bytes() / world + kv_bytes) / (peaks["hbm_gbs"] * 1e9) * 1e3
+    return {"workload": f"{cfg.name} verify only, TP={world}, batch {B}, prefix {prefix} (N(0,1) KV), k={k}, {M} tokens/forward",
+            "verify_us": ms * 1e3, "tensor_floor_ms": tensor_floor_ms, "hbm_floor_ms": hbm_floor_ms,
+            "frac_of_tensor_floor": tensor_floor_ms / ms, "tflops_per_gpu": (gemm_flops + attn_flops) / (ms * 1e-3) / 1e12,
+            "verified_tokens_per_second": M / (ms * 1e-3), "tp_error": int(tp_err),
+            "breakdown_ms_profiled": {c: round(v[0], 3) for c, v in prof.items()},
+            "allreduce_bytes_per_boundary": M * cfg.hidden_size * 4, "boundaries": 2 * cfg.num_hidden_layers}
+
+
+def companions(torch, dev, peak):
+    """Single-GPU companions of the measured CPU baselines of the reference arm (same inputs, same units)."""
+    import numpy as np
+    from asd_b200.algorithms import dp_solver
+    from asd_b200.engine import QwenEngine, SpecDecoder
+    from asd_b200.models.qwen2 import QWEN25
+    from asd_b200.ops import RejectionSampler
+    out = {}
+    # stop rule: the same 10^5 triples (L = 4 rows; L = 3 rows carry p = 1, C = 0 in the unused stage... kept simple:
+    # two launches, one per L), Bayesian shrinkage on the device path via risk_adjustment
+    rng = np.random.default_rng(7)
+    n = 100_000
+    lam = torch.from_numpy(rng.choice([0.1, 0.5, 1.0, 2.0, 5.0, 10.0], n)).to(dev)
+    p = torch.from_numpy(rng.random((n, 4))).to(dev)
+    C = torch.tensor([1.0, 2.0, 4.5, 10.0], dtype=torch.float64, device=dev).expand(n, 4).contiguous()
+    p[:, 3] = 1.0
+    for _ in range(3):
+        dp_solver.stop_rule_rows(p, C, lam, True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(10):
+        k_star, _ = dp_solver.stop_rule_rows(p, C, lam, True)
+    ev[1].record()
+    torch.cuda.synchronize()
+    out["stop_rule"] = {"decisions_per_second": n / (ev[0].elapsed_time(ev[1]) / 10 * 1e-3), "n": n,
+                        "what": "asd_stop_rule_rows on the device, one launch for all rows"}
+    grid = []
+    for B, k in ((1, 8), (16, 5), (64, 8), (256, 8)):
+        V, T = 152064, 0.7
+        g = torch.Generator(device=dev).manual_seed(4321)
+        tl = torch.randn(B, k + 1, V, device=dev, generator=g) * 2
+        dl = (tl[:, :k] + torch.randn(B, k, V, device=dev, generator=g)).contiguous()
+        dt = dl.argmax(-1).int()
+        ua = torch.rand(B, k, dtype=torch.float64, device=dev, generator=g)
+        ur = torch.rand(B, dtype=torch.float64, device=dev, generator=g)
+        smp = RejectionSampler(B, k, dev)
+        flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
+        times = []
+        for it in range(8):
+            flush.zero_()                                 # L2 flush between timed launches
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            smp(tl, dl, dt, ua, ur, T)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+        us = sorted(times)[len(times) // 2] * 1e3
+        nbytes = B * k * 2 * V * 4 + B * V * 4
+        grid.append({"B": B, "k": k, "V": V, "us": us, "GB_per_s": nbytes / us / 1e3, "hbm_frac": nbytes / us / 1e3 / peak})
+        del tl, dl, flush
+    out["sampler"] = {"grid": grid, "what": "asd_reject_sample, L2 flushed between launches, median of 5"}
+    torch.cuda.empty_cache()
+    # configs[0]: 0.5B -> 1.5B, k = 4, batch 1, greedy
+    t = QwenEngine(QWEN25["1.5b"], max_seqs=1, max_seq_len=1024, max_tokens=64, device=dev).load_random(seed=1)
+    d = QwenEngine(QWEN25["0.5b"], max_seqs=1, max_seq_len=1024, max_tokens=64, device=dev).load_random(seed=0)
+    dec = SpecDecoder(t, d, 1, 4, 0.0)
+    dec.prefill(torch.randint(0, QWEN25["1.5b"].vocab_size, (1, 64), generator=torch.Generator().manual_seed(1234)))
+    for _ in range(3):
+        dec.step()
+    em = torch.zeros((), dtype=torch.int64, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(32):
+        em += (dec.step()["accepted_len"].to(torch.int64) + 1).sum()
+    ev[1].record()
+    torch.cuda.synchronize()
+    out["config1"] = {"value": int(em.item()) / (ev[0].elapsed_time(ev[1]) * 1e-3), "unit": "tok/s", "steps": 32,
+                      "what": "Qwen2.5-0.5B -> Qwen2.5-1.5B, chain k=4, batch 1, greedy, 64-token prompt, on the GPU"}
+    t.close()
+    d.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def stage_generate_record(torch, wl, dev, max_tokens=96):
+    """the reference-facing seam itself: Stage.generate(prompts: list[str]) -> texts, on the bench's workload
+    (strings in, strings out; prefill, detokenisation and the per-request bookkeeping included)"""
+    from asd_b200.models.stage import Stage
+    B, prefix, k, T = wl["B"], wl["prefix"], wl["k"], wl["T"]
+    gpu = dev.index or 0
+    small = Stage("bench-draft", "7b", config=wl["draft"], seed=0, max_batch=B, max_model_len=prefix * 2 + 256, k=k, gpu_ids=[gpu])
+    big = Stage("bench-target", "32b", config=wl["target"], seed=1, draft=small, max_batch=B, max_model_len=prefix * 2 + 256,
+                k=k, gpu_ids=[gpu])
+    import random
+    rnd = random.Random(1234)
+    prompts = ["".join(chr(rnd.randrange(97, 123)) for _ in range(prefix)) for _ in range(B)]   # byte tokenizer: 1 token / char
+    big.generate(prompts[:B], max_tokens=8, temperature=T)                                          # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    texts, lps, st = big.generate(prompts, max_tokens=max_tokens, temperature=T)
+    dt = time.perf_counter() - t0
+    n = sum(len(lp) for lp in lps)
+    rec = {"value": n / dt, "unit": "tok/s", "wall_seconds": dt, "tokens": n, "decode_steps": st["decode_steps"],
+           "api": "Stage.generate(prompts=[str]*16, max_tokens, temperature) -> (texts, logprobs, stats)",
+           "includes": f"tokenisation, ragged prefill of {B} x {prefix} tokens on both models, decode, detokenisation"}
+    big.engine.close()
+    small.engine.close()
+    return rec
+
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -222,15 +476,19 @@ def run_ours(args):
         e.set_option("profile", 0)
     ps = max(args.profile_steps, 1)
 
+    tpc = tp_check(torch, dist, rank, world, dev, dec, target, wl["target"]) if world > 1 else None
+
     # max over ranks
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = t.tolist()
 
+    line = None
+    peak, peak_src = load_peaks()
     if rank == 0:
-        peak, peak_src = load_peaks()
         tcfg, dcfg = wl["target"], wl["draft"]
+        traffic = load_traffic()
         gemm_ms, gemm_n = prof_t["gemm"][0] / ps, prof_t["gemm"][1] / ps
         head_ms = prof_t["lm_head"][0] / ps
         layer_bytes = (tcfg.streamed_bytes() - 2 * tcfg.vocab_size * tcfg.hidden_size) / world
@@ -265,9 +523,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": roof_kernel,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
-                         # dram__bytes_read + dram__bytes_write of the four GEMM launches of one 32B layer, ncu --set
-                         # full (profiles/ncu_gemm_verify_r01_v4.txt): 998.3 MB vs 975.2 MB algorithmic = 1.024 x
-                         "traffic": (layer_bytes + head_bytes) * 1.024 if (world == 1 and args.workload == "32b") else None,
+                         # measured dram__bytes_read + dram__bytes_write of the committed `ncu --set full` capture of
+                         # these launches (profiles/traffic.json names the capture and the commit), per forward
+                         "traffic": ((layer_bytes + head_bytes) * traffic["dram_bytes_per_algorithmic_byte"]
+                                     if (traffic and world == 1 and args.workload == "32b") else None),
+                         "traffic_source": traffic["source"] if traffic else None,
                          "bytes_per_forward": layer_bytes + head_bytes, "ms_per_forward": roof_ms},
             "verify_step_us": verify_ms_timed * 1e3, "draft_step_us": draft_ms * 1e3,
             "verify_step_hbm_frac": (tcfg.streamed_bytes() / world + kv_bytes) / (verify_ms_timed * 1e-3) / 1e9 / peak,
@@ -276,19 +536,43 @@ def run_ours(args):
             "draft_breakdown_ms": {c: round(v[0] / ps / max(k, 1), 4) for c, v in prof_d.items()},
             "step_hbm_frac": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak,
         }
+        if tpc is not None:
+            line["tp_check"] = tpc
+    # ---- the main engines are done: free them before the companion measurements
+    dec = None
+    target.close()
+    draft.close()
+    target = draft = None
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if world > 1 and not args.no_config5:
+        import json as _json
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = _json.load(f)
+        c5 = config5(torch, dist, rank, world, dev, args, peaks)
+        if rank == 0:
+            line["config5"] = c5
+    if rank == 0:
+        if world == 1 and not args.no_companions:
+            line["companions"] = companions(torch, dev, peak)
+            line["stage_generate"] = stage_generate_record(torch, wl, dev)
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             from oracle.cpu_baseline import spec_step_baseline
             oracle.build()
             r = spec_step_baseline(tcfg, dcfg, B, k, prefix, T, sample_layers=1, threads=os.cpu_count())
             line["cpu_baseline"] = {"value": r["tokens_per_step"] / r["step_seconds"], "unit": UNIT,
-                                    "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+                                    "cores": r["threads"], "kind": "port", "sample": r["sample"], "extrapolated": True}
         print(json.dumps(line), flush=True)
     if comm is not None:
         barrier()
         comm.destroy()
     if world > 1:
         dist.destroy_process_group()
+    if tpc is not None and rank == 0 and not tpc.get("ok", False):
+        sys.stderr.write(f"tensor-parallel parity check FAILED: {tpc}\n")
+        sys.exit(3)
 
 
 def main():
@@ -304,6 +588,8 @@ def main():
     ap.add_argument("--temperature", type=float, default=0.7)
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-companions", action="store_true", help="skip the stop-rule / sampler-grid / config-1 / Stage.generate records")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the 72B verify-only record (BASELINE configs[4])")
     ap.add_argument("--no-fuse-norm", action="store_true", help="separate add+RMSNorm kernels instead of the fused epilogues")
     ap.add_argument("--nccl-only", action="store_true", help="TP boundaries through ncclAllReduce instead of the fused kernel")
     ap.add_argument("--opt", action="append", help="engine option name=value (e.g. pdl=0, attn_impl=0)")

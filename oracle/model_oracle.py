@@ -33,10 +33,12 @@ def inv_freq(head_dim: int, theta: float) -> torch.Tensor:
 
 
 @torch.no_grad()
-def qwen2_forward(w: dict, cfg, input_ids: torch.Tensor, positions: torch.Tensor | None = None) -> torch.Tensor:
+def qwen2_forward(w: dict, cfg, input_ids: torch.Tensor, positions: torch.Tensor | None = None,
+                  last_n: int | None = None) -> torch.Tensor:
     """w: HF-named state dict (any float dtype, used in fp32); cfg has hidden_size, num_hidden_layers,
     num_attention_heads, num_key_value_heads, head_dim, rms_norm_eps, rope_theta.
-    input_ids [B, T] -> logits fp32 [B, T, V]."""
+    input_ids [B, T] -> logits fp32 [B, T, V] (``last_n``: only the last n positions, [B, n, V] - the lm_head
+    of a 152K vocabulary over every prefix position is most of the oracle's time at the BASELINE shapes)."""
     B, T = input_ids.shape
     nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
     f = lambda name: w[name].float()
@@ -62,6 +64,8 @@ def qwen2_forward(w: dict, cfg, input_ids: torch.Tensor, positions: torch.Tensor
         h = rms_norm(x, f(p + "post_attention_layernorm.weight"), cfg.rms_norm_eps)
         g = torch.nn.functional.silu(h @ f(p + "mlp.gate_proj.weight").T) * (h @ f(p + "mlp.up_proj.weight").T)
         x = x + g @ f(p + "mlp.down_proj.weight").T
+    if last_n is not None:
+        x = x[:, -last_n:]
     x = rms_norm(x, f("model.norm.weight"), cfg.rms_norm_eps)
     head = w.get("lm_head.weight", w["model.embed_tokens.weight"]).float()
     return x @ head.T

@@ -320,3 +320,31 @@ def test_predictor_training_on_saved_rows(tmp_path):
     with pytest.raises(ValueError):
         train_quality_predictor(X, y, {"predictor": {"model": {"input_dim": 128}}})
     json.dumps({k: v for k, v in res.items() if k != "state_dict"})              # the report part is JSON-serialisable
+
+
+def test_gpu_placement_rules_follow_the_reference():
+    """src/config/model_config.py:136-150: len(gpu_ids) == tensor_parallel_size, no GPU shared between stages"""
+    from asd_b200.models.stage import ModelLoadError, validate_gpu_assignment
+    validate_gpu_assignment([("7b", 1, [0]), ("14b", 1, [1]), ("32b", 2, [2, 3]), ("72b", 4, [4, 5, 6, 7])])
+    with pytest.raises(ModelLoadError, match="doesn't match tensor_parallel_size"):
+        validate_gpu_assignment([("32b", 2, [2])])
+    with pytest.raises(ModelLoadError, match="multiple stages"):
+        validate_gpu_assignment([("7b", 1, [0]), ("32b", 2, [0, 1])])
+    with pytest.raises(ModelLoadError, match="duplicate"):
+        validate_gpu_assignment([("32b", 2, [1, 1])])
+
+
+def test_safetensors_round_trip(tmp_path):
+    import torch
+    from asd_b200.models.qwen2 import load_safetensors_dir, random_hf_weights, save_safetensors, tiny_config
+    w = random_hf_weights(tiny_config(num_hidden_layers=1), seed=4)
+    w["extra.f32"] = torch.arange(6, dtype=torch.float32).reshape(2, 3)
+    keys = sorted(w)
+    save_safetensors({k: w[k] for k in keys[:5]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_safetensors({k: w[k] for k in keys[5:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    back = load_safetensors_dir(str(tmp_path))
+    assert sorted(back) == keys
+    for k in keys:
+        assert back[k].dtype == w[k].dtype and torch.equal(back[k], w[k]), k
+    with pytest.raises(FileNotFoundError):
+        load_safetensors_dir(str(tmp_path / "nothing"))

@@ -135,3 +135,11 @@ def test_first_reject_prefix_property_full_size():
     ref = oracle.reject_sample(tl[idx].cpu().numpy(), dl[idx].cpu().numpy(), dtn[idx], ua[idx].cpu().numpy(),
                                ur[idx].cpu().numpy(), T)
     assert np.array_equal(ref["accepted_len"], n[idx]) and np.array_equal(ref["out_tokens"], toks[idx])
+
+
+@pytest.mark.parametrize("B", [64, 128, 256])
+def test_full_batch_every_row_against_oracle(B):
+    """BASELINE config-2 batch sizes at k = 8, V = 152064: EVERY sequence compared with the C oracle"""
+    k, V, T = 8, 152064, 0.7
+    tl, dl, dt, ua, ur = make_case(B, k, V, seed=500 + B, T=T)
+    compare(run_gpu(tl, dl, dt, ua, ur, T), oracle.reject_sample(tl, dl, dt, ua, ur, T))

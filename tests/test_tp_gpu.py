@@ -29,7 +29,7 @@ def _worker(rank, world, port, mode, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     cfg = Qwen2Config(512, 2, 8, 2, 1024, 4096, head_dim=128, name="tp-test")
-    w = random_hf_weights(cfg, seed=11)
+    w = random_hf_weights(cfg, seed=11, logit_std=0.4)
     ids = torch.randint(0, cfg.vocab_size, (3, 70), generator=torch.Generator().manual_seed(5))
     dev = torch.device("cuda", rank)
     eng = QwenEngine(cfg, max_seqs=3, max_seq_len=96, max_tokens=64, tp_rank=rank, tp_size=world, device=dev)
@@ -53,7 +53,9 @@ def _worker(rank, world, port, mode, out):
         ref = qwen2_forward(w, cfg, ids)[:, 64:]
         got = ver.view(3, 6, -1).cpu()
         out["err"] = float((got - ref).abs().max())
-        out["agree"] = float((got.argmax(-1) == ref.argmax(-1)).float().mean())
+        top2 = ref.topk(2, -1).values
+        dec = (top2[..., 0] - top2[..., 1]) > 4e-2          # rows an implementation within 2e-2 can decide
+        out["agree"] = float((got.argmax(-1) == ref.argmax(-1))[dec].float().mean()) if dec.any() else 1.0
         out["identical"] = bool(all(torch.equal(gathered[0], g) for g in gathered))
         out["tp_error"] = eng.tp_error()
     dist.barrier()
@@ -67,5 +69,5 @@ def test_tp2_logits_match_oracle(mode):
     import torch.multiprocessing as mp
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
-    assert out["err"] <= 2e-2 and out["agree"] >= 0.99, dict(out)
+    assert out["err"] <= 2e-2 and out["agree"] >= 0.999, dict(out)
     assert out["identical"] and out["tp_error"] == 0, dict(out)
