@@ -113,7 +113,10 @@ class QwenEngine(_BatchOps):
                  fuse_norm: bool = True):
         if not torch.cuda.is_available():
             raise AsdError("QwenEngine needs a CUDA device (there is no CPU fallback)")
-        self.cfg, self.device = cfg, torch.device(device)
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.cfg, self.device = cfg, dev
         self.tp_rank, self.tp_size = tp_rank, tp_size
         self.max_seqs, self.max_seq_len, self.max_tokens, self.page_size = max_seqs, max_seq_len, max_tokens, page_size
         assert cfg.num_attention_heads % tp_size == 0 and cfg.num_key_value_heads % tp_size == 0
@@ -517,8 +520,12 @@ class SpecDecoder:
         if self.limit is not None:      # frozen sequences stop advancing: positions stay below this
             bound = min(bound, self.start_len + self.limit + k + 1)
         if bound > self.max_len:
-            raise AsdError(f"step would reach position {bound} but max_seq_len is {self.max_len} "
-                           "(raise max_model_len or lower max_tokens)")
+            # the host-side bound assumes every draft token of every step was accepted; before refusing, read the
+            # true longest sequence (one sync, only on this rare path) and tighten the bound
+            bound = int(self.pos.max().item()) + k + 1
+            if bound > self.max_len:
+                raise AsdError(f"step would reach position {bound} but max_seq_len is {self.max_len} "
+                               "(raise max_model_len or lower max_tokens)")
         if k > 0:
             # draft step 1 re-feeds the previous token so the draft KV is complete after an all-accept
             two = torch.stack([self.prev_tok, self.last_tok], 1)

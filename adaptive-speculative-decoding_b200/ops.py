@@ -23,6 +23,8 @@ class RejectionSampler:
     def __init__(self, B: int, k: int, device="cuda"):
         self.B, self.k = B, k
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         nbytes = lib().asd_reject_sample_workspace_bytes(B, k)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self.accept_mask = torch.empty(B, k, dtype=torch.uint8, device=self.device)

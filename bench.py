@@ -160,7 +160,8 @@ def tp_check(torch, dist, rank, world, dev, dec, target, tcfg):
     1. every rank's verify logits of the last timed step must be bit-identical (ranks stay in lock step without
        exchanging tokens only if they are), 2. no rank may have timed out waiting for a peer
        (asd_engine_tp_error), 3. a 2-layer model of the target's width is run on M = 96 tokens by the N-way sharded
-       engine and by a single-GPU engine on rank 0; their logits must agree far inside the bf16 tolerance."""
+       engine and by a single-GPU engine on rank 0; their logits must agree within the north-star tolerance
+       (max-abs <= 2e-2 at logit std 0.25; they differ by fp32 summation order, which flips bf16 roundings)."""
     from dataclasses import replace
     from asd_b200.engine import QwenEngine
     from asd_b200.models.qwen2 import random_hf_weights
@@ -173,7 +174,7 @@ def tp_check(torch, dist, rank, world, dev, dec, target, tcfg):
     err = torch.tensor([float(target.tp_error())], device=dev)
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
     cfg2 = replace(tcfg, num_hidden_layers=2)
-    w = random_hf_weights(cfg2, seed=3, device=dev, logit_std=0.4)      # same seed, same device type: same weights on all ranks
+    w = random_hf_weights(cfg2, seed=3, device=dev, logit_std=0.25)      # same seed, same device type: same weights on all ranks
     B, q = 16, 6
     ids = torch.randint(0, cfg2.vocab_size, (B, q), generator=torch.Generator().manual_seed(7)).to(dev).to(torch.int32)
     slots = torch.arange(B, dtype=torch.int32, device=dev)
@@ -192,7 +193,9 @@ def tp_check(torch, dist, rank, world, dev, dec, target, tcfg):
         ref = one.forward_uniform(ids, zero, slots, q)
         torch.cuda.synchronize()
         max_abs = float((got - ref).abs().max())
-        agree = float((got.argmax(-1) == ref.argmax(-1)).float().mean())
+        top2 = ref.topk(2, -1).values
+        dec = (top2[..., 0] - top2[..., 1]) > 4e-2          # rows an implementation within 2e-2 can decide
+        agree = float((got.argmax(-1) == ref.argmax(-1))[dec].float().mean()) if bool(dec.any()) else 1.0
         one.close()
     sh.close()
     del w
@@ -201,7 +204,7 @@ def tp_check(torch, dist, rank, world, dev, dec, target, tcfg):
     if rank == 0:
         out.update(max_abs_vs_tp1_sample=max_abs, argmax_agree_vs_tp1_sample=agree,
                    sample=f"2 layers of {tcfg.name} at M={B * q}, sharded x{world} vs one GPU")
-        out["ok"] = bool(identical and out["tp_error"] == 0 and max_abs <= 5e-3)
+        out["ok"] = bool(identical and out["tp_error"] == 0 and max_abs <= 2e-2 and agree >= 0.999)
     return out
 
 
