@@ -54,6 +54,7 @@ def lib() -> ctypes.CDLL:
         "asd_engine_peer_connect": (i32, [vp, i32]),
         "asd_bayesian_adjustment_host": (f64, [f64, f64, f64, f64]),
         "asd_linear_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "asd_linear_bf16_tc": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
         "asd_linear_plan": (i32, [i32, i32, i32, i32, vp, vp, vp]),
         "asd_engine_create": (vp, [vp]),
         "asd_engine_destroy": (None, [vp]),

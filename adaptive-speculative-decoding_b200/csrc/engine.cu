@@ -34,6 +34,10 @@ struct Layer {
 struct Plans {
     GemmPlan qkv, o, gu, down;
     CUtensorMap x_norm, x_attn, x_act;
+    // token counts above the HBM/tensor ridge: gate|up and down run on the tensor-bound CTA-pair kernel (gemm_tc.cu)
+    bool use_tc = false;
+    TcPlan gu_tc, down_tc;
+    CUtensorMap x_norm_tc, x_act_tc;
 };
 
 struct Engine {
@@ -57,6 +61,7 @@ struct Engine {
     size_t part_floats = 0, o_part_floats = 0;
     std::unordered_map<int, Plans> plans;
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
+    std::unordered_map<int, std::pair<TcPlan, CUtensorMap>> lm_plans_tc;
     // options
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1, tp_two_shot = 0;
@@ -123,6 +128,14 @@ static int ensure_plans(Engine* e, int M, Plans** out) {
     if (make_tmap_bf16(&p.x_norm, e->fuse_norm ? e->resid_bf : e->xnorm, M, h, h, p.qkv.MT)) return -1;
     if (make_tmap_bf16(&p.x_attn, e->attn, M, e->qdim, e->qdim, p.o.MT)) return -1;
     if (make_tmap_bf16(&p.x_act, e->act, M, e->c.ffn, e->c.ffn, p.down.MT)) return -1;
+    p.use_tc = e->tune.gemm_big && M > 256;
+    if (p.use_tc) {
+        if (gemm_tc_plan(&p.gu_tc, M, 2 * e->ffp, h, GEMM_OUT_SWIGLU, 0, e->force_stages)) return -1;
+        if (gemm_tc_plan(&p.down_tc, M, h, e->c.ffn, GEMM_OUT_F32, 0, e->force_stages)) return -1;
+        if ((size_t)p.down_tc.ksplit * M * h > e->part_floats) return set_error("engine: split-K workspace too small");
+        if (make_tmap_bf16(&p.x_norm_tc, e->fuse_norm ? e->resid_bf : e->xnorm, M, h, h, p.gu_tc.MT / 2)) return -1;
+        if (make_tmap_bf16(&p.x_act_tc, e->act, M, e->c.ffn, e->c.ffn, p.down_tc.MT / 2)) return -1;
+    }
     auto r = e->plans.emplace(M, p);
     *out = &r.first->second;
     return 0;
@@ -186,6 +199,62 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         if (P->qkv.mode == GEMM_OUT_QKV && launch_rope_table(positions, e->inv_freq, e->rope_cs, M, hd / 2, s)) return -1;
     }
     // residual update after a row-parallel projection: fused into the GEMM when possible, else glue kernel
+    // one kernel: all-reduce of the partials in tp_buf[epoch & 1] over NVLink peer memory + residual add + norm stats
+    auto peer_allreduce = [&](const __nv_bfloat16* next_ln) -> int {
+        PROF(PROF_COMM);
+        parts = 1;
+        const uint32_t ep = e->tp_epoch;   // the GEMM above wrote tp_buf[ep & 1]
+        // two-shot (option tp_two_shot = 1): a row is reduced by its home rank and fetched once by the others, so a
+        // rank moves 2 (W-1)/W payloads instead of W-1 (TP8, 96 tokens: 3.4 MB instead of 13.8 MB per boundary).
+        // Measured on 8 B200: 12.4 ms per verify forward against 11.1 ms one-shot - at these sizes the exchange is
+        // bound by the second flag hop (fence.sys + release), not by bytes - so one-shot stays the default.
+        // It pays once bytes dominate: saved traffic (W-1 - 2 (W-1)/W) * M * hidden * 4 >= 16 MB per boundary
+        // (72B, 576 tokens, TP4: 56 -> 28 MB per boundary).  tp_two_shot = 1 forces it, -1 disables it.
+        const double payload = (double)M * h * 4.0, w1 = c.tp_size - 1;
+        const bool two = (e->tp_two_shot == 1 && M <= kTpRowFlags) ||
+                         (e->tp_two_shot == 0 && M <= kTpRowFlags &&
+                          (w1 - 2.0 * w1 / c.tp_size) * payload >= 16.0 * (1 << 20));
+        const float* bc[8] = {};
+        uint32_t* rf[8] = {};
+        for (int r = 0; r < c.tp_size; ++r) {
+            bc[r] = e->peer_buf[ep & 1][r] + 2 * Mx * (size_t)h;   // slot 1 of the receive buffer: the final rows
+            rf[r] = e->peer_flags[r] + 64;
+        }
+        return launch_tp_allreduce_norm(e->peer_buf[ep & 1], e->peer_flags, c.tp_rank, c.tp_size, ep, e->tp_error,
+                                        e->resid, next_ln, fn ? nullptr : (next_ln ? e->xnorm : nullptr), M, h,
+                                        c.rms_eps, fn ? e->resid_bf : nullptr, fn ? e->sumsq : nullptr, s,
+                                        two ? bc : nullptr, two ? rf : nullptr);
+    };
+    // row-parallel projection on the tensor-bound kernel: fp32 K-split slices, summed in order by the glue kernels
+    auto project_residual_tc = [&](const TcPlan& pl, const CUtensorMap& tw, const CUtensorMap& tx,
+                                   const __nv_bfloat16* next_ln) -> int {
+        const bool p2p_ok = tp && e->p2p;
+        const size_t stride = (size_t)M * h;
+        if (p2p_ok) ++e->tp_epoch;
+        float* dst = (p2p_ok && pl.ksplit == 1) ? e->tp_buf[e->tp_epoch & 1] : e->part;
+        {
+            PROF(PROF_GEMM);
+            if (gemm_tc_launch(pl, tw, tx, dst, h, h, stride, e->pdl, s, false, nullptr)) return -1;
+        }
+        if (p2p_ok) {
+            if (pl.ksplit > 1) {
+                PROF(PROF_GLUE);
+                if (launch_reduce_slices(e->part, pl.ksplit, stride, stride, s, e->tp_buf[e->tp_epoch & 1])) return -1;
+            }
+            return peer_allreduce(next_ln);
+        }
+        int ns = pl.ksplit;
+        if (tp) {
+            PROF(PROF_COMM);
+            if (tp_allreduce(e, e->part, ns, stride, stride, s)) return -1;
+            ns = 1;
+        }
+        PROF(PROF_GLUE);
+        parts = 1;
+        return launch_add_norm(e->resid, e->part, ns, stride, nullptr, nullptr, next_ln,
+                               fn ? nullptr : (next_ln ? e->xnorm : nullptr), M, h, c.rms_eps, s,
+                               fn ? e->resid_bf : nullptr, fn ? e->sumsq : nullptr);
+    };
     auto project_residual = [&](const GemmPlan& pl, const CUtensorMap& tw, const CUtensorMap& tx,
                                 const __nv_bfloat16* next_ln) -> int {
         const bool fuse = !tp && (pl.reduce || pl.ksplit == 1);
@@ -238,32 +307,7 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             return 0;
         }
         int ns = fuse ? 0 : (pl.reduce ? 1 : pl.ksplit);
-        if (tp && p2p_ok) {
-            // one kernel: all-reduce over NVLink peer memory + residual add + norm statistics
-            PROF(PROF_COMM);
-            parts = 1;
-            const uint32_t ep = e->tp_epoch;   // the GEMM above wrote tp_buf[ep & 1]
-            // two-shot (option tp_two_shot = 1): a row is reduced by its home rank and fetched once by the others, so a
-            // rank moves 2 (W-1)/W payloads instead of W-1 (TP8, 96 tokens: 3.4 MB instead of 13.8 MB per boundary).
-            // Measured on 8 B200: 12.4 ms per verify forward against 11.1 ms one-shot - at these sizes the exchange is
-            // bound by the second flag hop (fence.sys + release), not by bytes - so one-shot stays the default.
-            // It pays once bytes dominate: saved traffic (W-1 - 2 (W-1)/W) * M * hidden * 4 >= 16 MB per boundary
-            // (72B, 576 tokens, TP4: 56 -> 28 MB per boundary).  tp_two_shot = 1 forces it, -1 disables it.
-            const double payload = (double)M * h * 4.0, w1 = c.tp_size - 1;
-            const bool two = (e->tp_two_shot == 1 && M <= kTpRowFlags) ||
-                             (e->tp_two_shot == 0 && M <= kTpRowFlags &&
-                              (w1 - 2.0 * w1 / c.tp_size) * payload >= 16.0 * (1 << 20));
-            const float* bc[8] = {};
-            uint32_t* rf[8] = {};
-            for (int r = 0; r < c.tp_size; ++r) {
-                bc[r] = e->peer_buf[ep & 1][r] + 2 * Mx * (size_t)h;   // slot 1 of the receive buffer: the final rows
-                rf[r] = e->peer_flags[r] + 64;
-            }
-            return launch_tp_allreduce_norm(e->peer_buf[ep & 1], e->peer_flags, c.tp_rank, c.tp_size, ep, e->tp_error,
-                                            e->resid, next_ln, fn ? nullptr : (next_ln ? e->xnorm : nullptr), M, h,
-                                            c.rms_eps, fn ? e->resid_bf : nullptr, fn ? e->sumsq : nullptr, s,
-                                            two ? bc : nullptr, two ? rf : nullptr);
-        }
+        if (tp && p2p_ok) return peer_allreduce(next_ln);
         if (tp) {
             PROF(PROF_COMM);
             if (tp_allreduce(e, e->part, ns, (size_t)M * h, (size_t)M * h, s)) return -1;
@@ -340,7 +384,11 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         }
         gemm_set_next(P->gu, &L.t_gu);
         if (project_residual(P->o, L.t_o, P->x_attn, L.ln2)) return -1;
-        {
+        if (P->use_tc) {
+            PROF(PROF_GEMM);
+            if (gemm_tc_launch(P->gu_tc, L.t_gu, P->x_norm_tc, e->act, c.ffn, c.ffn, 0, e->pdl, s, false, consumer(e->sumsq)))
+                return -1;
+        } else {
             PROF(PROF_GEMM);
             gemm_set_next(P->down, &L.t_down);
             if (gemm_launch(P->gu, L.t_gu, P->x_norm, e->act, c.ffn, c.ffn, e->pdl, s, false, nullptr,
@@ -350,7 +398,10 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         const bool last = l + 1 == c.n_layers;
         const __nv_bfloat16* wn = last ? e->final_norm : e->layers[l + 1].ln1;
         if (!last) gemm_set_next(P->qkv, &e->layers[l + 1].t_qkv);
-        if (project_residual(P->down, L.t_down, P->x_act, (last && n_logit_rows == 0 && !fn) ? nullptr : wn)) return -1;
+        const __nv_bfloat16* down_ln = (last && n_logit_rows == 0 && !fn) ? nullptr : wn;
+        if (P->use_tc ? project_residual_tc(P->down_tc, L.t_down, P->x_act_tc, down_ln)
+                      : project_residual(P->down, L.t_down, P->x_act, down_ln))
+            return -1;
     }
     if (n_logit_rows <= 0) return 0;
     if (!logits_out) return set_error("engine: logits_out is NULL");
@@ -368,6 +419,19 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         key = -rows;
     } else if (n_logit_rows != M) {
         return set_error("engine: n_logit_rows must equal M when logit_rows is NULL");
+    }
+    if (e->tune.gemm_big && rows > 256) {   // tensor-bound kernel; 152K vocabulary rows give plenty of units without a K split
+        auto jt = e->lm_plans_tc.find(key);
+        if (jt == e->lm_plans_tc.end()) {
+            std::pair<TcPlan, CUtensorMap> v;
+            if (gemm_tc_plan(&v.first, rows, c.vocab, h, GEMM_OUT_F32, 1, e->force_stages)) return -1;
+            if (make_tmap_bf16(&v.second, src, rows, h, h, v.first.MT / 2)) return -1;
+            jt = e->lm_plans_tc.emplace(key, v).first;
+        }
+        PROF(PROF_LMHEAD);
+        const int ld = logits_ld > 0 ? (int)logits_ld : c.vocab;
+        return gemm_tc_launch(jt->second.first, e->t_lm, jt->second.second, logits_out, ld, c.vocab, 0, e->pdl, s, false,
+                              consumer(ss));
     }
     auto it = e->lm_plans.find(key);
     if (it == e->lm_plans.end()) {
@@ -649,6 +713,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else return set_error("asd_engine_set_option: unknown option %s", name);
     e->plans.clear();
     e->lm_plans.clear();
+    e->lm_plans_tc.clear();
     return 0;
 }
 

@@ -77,4 +77,15 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
                 int n_valid, bool pdl, cudaStream_t stream, bool accumulate = false,
                 const QkvEpilogue* qkv = nullptr, const NormFusion* norm = nullptr, const TpFusion* tp = nullptr);
 
+// ---- tensor-bound 2-CTA kernel (gemm_tc.cu): token counts above the HBM/tensor ridge
+struct TcPlan {
+    int M, N, K, mode;
+    int MT, m_tiles, w_tiles, kblocks, ksplit, stages, smem_bytes, pairs;
+};
+int gemm_tc_plan(TcPlan* pl, int M, int N, int K, int mode, int force_ksplit, int force_stages);
+// x tensor map: box rows = MT / 2 (each CTA of the pair loads half of the token tile); w tensor map: box rows = 128.
+// GEMM_OUT_F32: out fp32 [ksplit][slice_stride] slices of [M][ldo]; GEMM_OUT_SWIGLU: out bf16 [M][ldo].
+int gemm_tc_launch(const TcPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap& tmap_x, void* out, int ldo, int n_valid,
+                   size_t slice_stride, bool pdl, cudaStream_t stream, bool accumulate, const NormFusion* norm);
+
 }  // namespace asd

@@ -297,7 +297,10 @@ int launch_tp_allreduce_norm(const float* const* peer_bufs, uint32_t* const* pee
 }
 
 // reduce K-split slices into slice 0 (used before a tensor-parallel all-reduce)
-__global__ void reduce_slices_kernel(float* __restrict__ part, int nslices, size_t slice_stride, size_t n) {
+__global__ void reduce_slices_kernel(float* __restrict__ part, int nslices, size_t slice_stride, size_t n,
+                                     float* __restrict__ dst) {
+    grid_dep_wait();
+    grid_dep_launch();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i * 4 >= n) return;
     float4 a = reinterpret_cast<float4*>(part)[i];
@@ -308,14 +311,15 @@ __global__ void reduce_slices_kernel(float* __restrict__ part, int nslices, size
         a.z += p.z;
         a.w += p.w;
     }
-    reinterpret_cast<float4*>(part)[i] = a;
+    reinterpret_cast<float4*>(dst)[i] = a;
 }
 
-int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream) {
-    if (nslices <= 1 || n == 0) return 0;
+int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream, float* dst) {
+    if (dst == nullptr) dst = part;
+    if ((nslices <= 1 && dst == part) || n == 0) return 0;
     const int threads = 256;
     const size_t blocks = (n / 4 + threads - 1) / threads;
-    reduce_slices_kernel<<<(unsigned)blocks, threads, 0, stream>>>(part, nslices, slice_stride, n);
+    reduce_slices_kernel<<<(unsigned)blocks, threads, 0, stream>>>(part, nslices, slice_stride, n, dst);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

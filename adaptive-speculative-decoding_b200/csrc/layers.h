@@ -15,7 +15,9 @@ int launch_tp_allreduce_norm(const float* const* peer_bufs, uint32_t* const* pee
                              uint32_t epoch, int* error, float* resid, const __nv_bfloat16* w, __nv_bfloat16* xnorm,
                              int M, int h, float eps, __nv_bfloat16* resid_bf, float* sumsq0, cudaStream_t stream,
                              const float* const* peer_bcast = nullptr, uint32_t* const* peer_rowflags = nullptr);
-int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream);
+// sums the slices in order into dst (nullptr: into slice 0)
+int launch_reduce_slices(float* part, int nslices, size_t slice_stride, size_t n, cudaStream_t stream,
+                         float* dst = nullptr);
 int launch_qkv_rope(const float* part, int nslices, size_t slice_stride, const __nv_bfloat16* bias,
                     const int* positions, const int* token_slot, const int* page_table, int max_pages,
                     const float* inv_freq, __nv_bfloat16* q_out, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int M,

@@ -115,6 +115,30 @@ def linear_bf16(x: torch.Tensor, w: torch.Tensor, out_mode: int = 0, ksplit: int
     return out
 
 
+def linear_bf16_tc(x: torch.Tensor, w: torch.Tensor, out_mode: int = 0, ksplit: int = 0, stages: int = 0):
+    """Y = X @ W^T on the tensor-bound CTA-pair kernel (``asd_linear_bf16_tc``).  out_mode 0 -> fp32 [M, N] (the
+    K-split slices are summed here in order, as the glue kernels do); 2 -> SwiGLU bf16 [M, N/2]."""
+    assert x.is_cuda and w.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    x, w = x.contiguous(), w.contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    used = ctypes.c_int(0)
+    if out_mode == 2:
+        out = torch.empty(M, N // 2, dtype=torch.bfloat16, device=x.device)
+    else:
+        out = torch.empty(8, M, N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib().asd_linear_bf16_tc(x.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, out_mode, ksplit, stages,
+                                      ctypes.byref(used), _stream())
+    check(rc, "asd_linear_bf16_tc")
+    if out_mode == 2:
+        return out
+    acc = out[0].clone()
+    for s in range(1, used.value):
+        acc += out[s]
+    return acc
+
+
 def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
     """[ff, K] gate and up weights -> [2*ceil(ff/64)*64, K] with 64 gate rows then 64 up rows per
     128-row tile (zero rows pad ff to a multiple of 64): the layout asd_linear_bf16 mode 2 expects."""

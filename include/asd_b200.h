@@ -102,6 +102,11 @@ ASD_API double asd_bayesian_adjustment_host(double p_hat, double n_obs, double a
  */
 ASD_API int asd_linear_bf16(const void* x, const void* w, void* out, int M, int N, int K, int out_mode, int ksplit,
                     int stages, int* ksplit_used, void* stream);
+/* Same contraction on the tensor-bound kernel used above the HBM/tensor ridge (M > 256 tokens: BASELINE configs[4],
+ * prefill): CTA pairs (tcgen05 cta_group::2, 256 weight rows x <= 256 tokens per tile), persistent, two TMEM
+ * accumulators.  out_mode 0: fp32 [ksplit_used, M, N] slices; out_mode 2: SwiGLU bf16 [M, N/2]. */
+ASD_API int asd_linear_bf16_tc(const void* x, const void* w, void* out, int M, int N, int K, int out_mode, int ksplit,
+                       int stages, int* ksplit_used, void* stream);
 ASD_API int asd_linear_plan(int M, int N, int K, int out_mode, int* ksplit, int* stages, int* token_tile);
 
 /* ---------------------------------------------------------------------------------------------

@@ -210,3 +210,30 @@ def test_spec_decode_sampling_runs_and_self_draft_accepts_everything():
     # draft rows are computed at M = B (or 2B), target rows at M = B*(k+1): identical weights give the
     # same logits up to fp32 summation order, so p/q = 1 +- 1e-5 and u <= p/q except for u within 1e-5 of 1
     assert tot >= 6 * B * k - 1
+
+
+@pytest.mark.parametrize("fuse_norm", [True, False])
+def test_engine_large_m_takes_the_tensor_bound_kernel(fuse_norm):
+    """M = 320 tokens per forward (> 256): gate|up, down and lm_head run on the CTA-pair kernel (gemm_tc.cu),
+    whose K-split slices are summed by the glue kernels; same oracle, same bar, and the same answer (to fp32
+    summation order) as the weight-streaming kernels (option gemm_big = 0)."""
+    from asd_b200.engine import QwenEngine
+    cfg = Qwen2Config(512, 2, 8, 2, 1024, 4096, head_dim=128, name="big-m")
+    w = random_hf_weights(cfg, seed=11, logit_std=0.4)
+    B, P, q = 40, 40, 8
+    ids = torch.randint(0, cfg.vocab_size, (B, P + q), generator=torch.Generator().manual_seed(5))
+    ref = qwen2_forward(w, cfg, ids)[:, P:]
+    outs = []
+    for big in (1, 0):
+        eng = QwenEngine(cfg, max_seqs=B, max_seq_len=P + q + 16, max_tokens=B * q, fuse_norm=fuse_norm).load_hf_weights(w)
+        eng.set_option("gemm_big", big)
+        slots = torch.arange(B, dtype=torch.int32, device="cuda")
+        idc = ids.cuda().to(torch.int32)
+        eng.prefill(idc[:, :P], slots, want_logits=False)
+        ver = eng.forward_uniform(idc[:, P:].contiguous(), torch.full((B,), P, dtype=torch.int32, device="cuda"), slots, P + q)
+        torch.cuda.synchronize()
+        outs.append(ver.view(B, q, -1).cpu())
+        eng.close()
+    check(outs[0], ref)
+    check(outs[1], ref)
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-2
