@@ -518,6 +518,8 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     }
     const int G = L.nh / L.nkv;
     const int rows = L.max_qlen * G;
+    if (L.impl == 2 && L.kv_map != nullptr && L.hd == 128 && L.page_size == 16 && rows <= 128)
+        return launch_attention_tc(L, stream);
     const int rg = (rows + 15) / 16;
     if (rg > 8) return set_error("attention: q_len * group = %d rows exceeds 128; chunk the query", rows);
     // key groups per row group: keep 4-8 warps per CTA so that one CTA per SM still hides latency

@@ -47,6 +47,8 @@ struct Engine {
     const __nv_bfloat16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
     const float* inv_freq = nullptr;
     CUtensorMap t_lm;
+    CUtensorMap kv_map;          // whole paged pool as rows of head_dim elements (tcgen05 attention)
+    bool kv_map_ok = false;
     __nv_bfloat16* kv_pool = nullptr;
     size_t kv_half = 0;  // elements of one K (or V) pool of one layer
     const int* page_table = nullptr;
@@ -63,7 +65,7 @@ struct Engine {
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     std::unordered_map<int, std::pair<TcPlan, CUtensorMap>> lm_plans_tc;
     // options
-    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
+    int attn_impl = 2, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1, tp_two_shot = 0;
     Tuning tune;   // per-engine knobs, installed for the calling thread by forward()
     int device = 0;
@@ -378,6 +380,9 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         A.split_keys = split_keys;
         A.nsplit_max = nsplit_max;
         A.impl = e->attn_impl;
+        A.kv_map = e->kv_map_ok ? &e->kv_map : nullptr;
+        A.k_row0 = (long long)(2 * l) * e->num_pages * nkv * c.page_size;
+        A.v_row0 = A.k_row0 + (long long)e->num_pages * nkv * c.page_size;
         {
             PROF(PROF_ATTN);
             if (launch_attention(A, s)) return -1;
@@ -572,6 +577,12 @@ int asd_engine_set_kv(asd_engine_t* h, void* kv_pool, int num_pages, const int32
     e->max_seqs = max_seqs;
     e->max_pages = max_pages_per_seq;
     e->kv_half = (size_t)num_pages * e->c.n_kv_heads * e->c.page_size * e->c.head_dim;
+    e->kv_map_ok = false;
+    const unsigned long long rows = 2ull * e->c.n_layers * num_pages * e->c.n_kv_heads * e->c.page_size;
+    if (e->c.head_dim == 128 && e->c.page_size == 16 && rows < (1ull << 31)) {
+        if (make_tmap_bf16(&e->kv_map, kv_pool, rows, 128, 128, 16)) return -1;
+        e->kv_map_ok = true;
+    }
     return 0;
 }
 

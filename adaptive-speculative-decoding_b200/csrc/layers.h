@@ -1,5 +1,6 @@
 // Host-side launchers of the non-GEMM kernels of the forward (layers.cu, attention.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -41,7 +42,14 @@ struct AttnLaunch {
     float* ml_part;
     int* tickets;           // [nseq * nkv] zero-initialised, self-resetting
     int M, nseq, max_qlen, nh, nkv, hd, page_size, max_pages, split_keys, nsplit_max, impl;
+    // impl 2 (tcgen05 kernel, attention_tc.cu): 2-D TMA map over the whole paged pool viewed as rows of head_dim
+    // elements (box = 64 elements x 16 positions) and the first row of this layer's K / V
+    const CUtensorMap* kv_map = nullptr;
+    long long k_row0 = 0, v_row0 = 0;
 };
+// impl 0: one-warp cross-check kernel; 1: mma.sync kernel; 2: tcgen05 kernel when the shape allows (head_dim 128,
+// 16-position pages, q_len * group <= 128), else 1
 int launch_attention(const AttnLaunch& L, cudaStream_t stream);
+int launch_attention_tc(const AttnLaunch& L, cudaStream_t stream);
 
 }  // namespace asd

@@ -383,6 +383,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     wl = workload(args)
+    if args.config5_only:       # development aid: only the 72B verify-only record
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        c5 = config5(torch, dist, rank, world, dev, args, peaks)
+        if rank == 0:
+            print(json.dumps({"config5": c5}), flush=True)
+        dist.destroy_process_group()
+        return
     B, k, prefix, T = wl["B"], wl["k"], wl["prefix"], wl["T"]
     n_steps_total = args.warmup + 2 * args.steps + args.profile_steps + 4
     max_len = prefix + n_steps_total * (k + 1) + 32
@@ -592,6 +600,7 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-companions", action="store_true", help="skip the stop-rule / sampler-grid / config-1 / Stage.generate records")
+    ap.add_argument("--config5-only", action="store_true", help="N > 1: only the 72B verify-only record")
     ap.add_argument("--no-config5", action="store_true", help="N > 1: skip the 72B verify-only record (BASELINE configs[4])")
     ap.add_argument("--no-fuse-norm", action="store_true", help="separate add+RMSNorm kernels instead of the fused epilogues")
     ap.add_argument("--nccl-only", action="store_true", help="TP boundaries through ncclAllReduce instead of the fused kernel")

@@ -50,7 +50,7 @@ def check(got, ref):
     assert agree >= ARGMAX, msg
 
 
-@pytest.mark.parametrize("attn_impl", [0, 1])
+@pytest.mark.parametrize("attn_impl", [0, 1, 2])
 @pytest.mark.parametrize("name,cfg,B,T,q", [
     ("tiny-hd64", tiny_config(), 3, 37, 5),
     ("g5-hd128", Qwen2Config(512, 2, 10, 2, 1024, 4096, head_dim=128, name="g5"), 4, 150, 6),
@@ -86,8 +86,9 @@ def test_engine_unfused_paths(opts):
     eng.close()
 
 
+@pytest.mark.parametrize("attn_impl", [1, 2])
 @pytest.mark.parametrize("min_keys,target", [(128, 592), (64, 2000), (256, 148)])
-def test_attention_key_splits(min_keys, target):
+def test_attention_key_splits(min_keys, target, attn_impl):
     """long sequences split their keys over several CTAs (flash-decoding); the last CTA merges the partials"""
     from asd_b200.engine import QwenEngine
     cfg = Qwen2Config(1024, 1, 8, 1, 512, 1024, head_dim=128, name="g8")
@@ -95,6 +96,7 @@ def test_attention_key_splits(min_keys, target):
     ids = torch.randint(0, cfg.vocab_size, (2, 700), generator=torch.Generator().manual_seed(5))
     ref = qwen2_forward(w, cfg, ids)
     eng = QwenEngine(cfg, max_seqs=2, max_seq_len=720, max_tokens=64).load_hf_weights(w)
+    eng.set_option("attn_impl", attn_impl)
     eng.set_option("attn_min_split_keys", min_keys)
     eng.set_option("attn_target_ctas", target)
     slots = torch.arange(2, dtype=torch.int32, device="cuda")
