@@ -65,7 +65,10 @@ struct Engine {
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     std::unordered_map<int, std::pair<TcPlan, CUtensorMap>> lm_plans_tc;
     // options
-    int attn_impl = 2, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
+    // attn_impl: 1 = mma.sync kernel (default: measured faster on every bench shape, tools/bench_attn.py), 2 = tcgen05
+    // kernel (attention_tc.cu; correct, but its single softmax warpgroup keeps it behind: 47 vs 22 us at 32B/prefix 512,
+    // 234 vs 179 us at 72B-TP4/prefix 4096), 0 = one-warp cross-check kernel
+    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1, tp_two_shot = 0;
     Tuning tune;   // per-engine knobs, installed for the calling thread by forward()
     int device = 0;
