@@ -19,6 +19,7 @@
 #include "asd_internal.h"
 #include "gemm.h"
 #include "layers.h"
+#include "persist.h"
 
 namespace asd {
 
@@ -71,6 +72,16 @@ struct Engine {
     int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1, tp_two_shot = 0;
     Tuning tune;   // per-engine knobs, installed for the calling thread by forward()
+    // persistent forward kernel (forward_persist.cu): one cooperative launch per forward when the shape allows
+    // measured on B200 (tools/trace_persist.py): the persistent kernel streams every GEMM at 87-95 % of HBM speed, but a
+    // phase boundary through global memory (partials -> flags -> reduce -> epilogue -> counter -> X load) costs 15-18 us
+    // against 10-12 us for a kernel boundary under programmatic dependent launch, so it is opt-in (option persist = 1)
+    int persist = 0, persist_ahead = 0;
+    PLayer* p_layers = nullptr;      // device array, rebuilt lazily after set_layer / set_kv
+    bool p_layers_ok = false;
+    unsigned* p_sync = nullptr;
+    float* p_ws = nullptr;
+    unsigned long long* p_trace = nullptr;   // optional (asd_debug_persist_trace)
     int device = 0;
     void* comm = nullptr;
     allreduce_fn_t allreduce = nullptr;
@@ -184,6 +195,47 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     const int nsplit_max = (max_kv_len + split_keys - 1) / split_keys;
     if ((size_t)M * nh * nsplit_max * hd > e->o_part_floats) return set_error("engine: attention workspace too small");
 
+    if (e->persist && !tp && fn && e->p_sync != nullptr &&
+        persist_supported(M, n_logit_rows, max_qlen, nh, nkv, hd, c.page_size, h, c.n_layers)) {
+        if (n_logit_rows > 0 && !logits_out) return set_error("engine: logits_out is NULL");
+        if (logit_rows == nullptr && n_logit_rows > 0 && n_logit_rows != M)
+            return set_error("engine: n_logit_rows must equal M when logit_rows is NULL");
+        if (!e->p_layers_ok) {
+            std::vector<PLayer> hl(c.n_layers);
+            for (int l = 0; l < c.n_layers; ++l) {
+                const Layer& Ly = e->layers[l];
+                memset(&hl[l], 0, sizeof(PLayer));
+                hl[l].t_qkv = Ly.t_qkv, hl[l].t_o = Ly.t_o, hl[l].t_gu = Ly.t_gu, hl[l].t_down = Ly.t_down;
+                hl[l].bqkv = Ly.bqkv, hl[l].ln1 = Ly.ln1, hl[l].ln2 = Ly.ln2;
+                hl[l].k_cache = e->kv_pool + (size_t)(2 * l) * e->kv_half;
+                hl[l].v_cache = hl[l].k_cache + e->kv_half;
+            }
+            // stream-ordered after every forward already enqueued on this stream; a forward on another stream must
+            // not be in flight while weights / the KV pool are being replaced (same rule as for the weights themselves)
+            ASD_CUDA(cudaMemcpyAsync(e->p_layers, hl.data(), sizeof(PLayer) * c.n_layers, cudaMemcpyHostToDevice, s));
+            ASD_CUDA(cudaStreamSynchronize(s));
+            e->p_layers_ok = true;
+        }
+        PersistLaunch PL;
+        PL.layers = e->p_layers;
+        PL.n_layers = c.n_layers, PL.h = h, PL.nqkv = e->nqkv, PL.qdim = e->qdim, PL.ffn = c.ffn, PL.ffp = e->ffp;
+        PL.vocab = c.vocab, PL.nh = nh, PL.nkv = nkv, PL.hd = hd, PL.page_size = c.page_size, PL.max_pages = e->max_pages;
+        PL.Mx = Mx, PL.eps = c.rms_eps;
+        PL.embed = e->embed, PL.final_norm = e->final_norm, PL.lm_head = e->lm_head, PL.inv_freq = e->inv_freq;
+        PL.page_table = e->page_table;
+        PL.M = M, PL.nseq = nseq, PL.max_qlen = max_qlen, PL.max_kv_len = max_kv_len;
+        PL.tokens = tokens, PL.positions = positions, PL.token_slot = token_slot, PL.cu_q = cu_q, PL.seq_slot = seq_slot;
+        PL.resid = e->resid, PL.resid_bf = e->resid_bf, PL.sumsq = e->sumsq, PL.sumsq_sel = e->sumsq_sel;
+        PL.rope_cs = e->rope_cs, PL.q = e->q, PL.attn = e->attn, PL.act = e->act, PL.xsel = e->xsel;
+        PL.split_keys = split_keys, PL.nsplit_max = nsplit_max;
+        PL.o_part = e->o_part, PL.ml_part = e->ml_part, PL.tickets = e->tickets;
+        PL.logit_rows = logit_rows, PL.n_logit_rows = n_logit_rows, PL.logits = logits_out;
+        PL.logits_ld = logits_ld > 0 ? logits_ld : c.vocab;
+        PL.prefetch_ahead = e->persist_ahead;
+        PL.sync = e->p_sync, PL.part_ws = e->p_ws, PL.error = e->tp_error, PL.trace = e->p_trace;
+        PROF(PROF_GEMM);
+        return persist_launch(PL, s);
+    }
     int parts = 1;   // rows of e->sumsq that currently describe the residual (fused-norm mode)
     NormFusion cons;  // consumer-side descriptor, refreshed before each consumer GEMM
     auto consumer = [&](const float* ss) -> const NormFusion* {
@@ -516,6 +568,13 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
             cudaMemset(e->tp_error, 0, 256);
         }
     }
+    if (c.tp_size == 1) {
+        alloc((void**)&e->tp_error, 256);       // device-side wait bound exceeded (persistent kernel)
+        if (ok) cudaMemset(e->tp_error, 0, 256);
+        alloc((void**)&e->p_layers, sizeof(PLayer) * c.n_layers);
+        alloc((void**)&e->p_sync, sizeof(unsigned) * kPersistSyncWords);
+        alloc((void**)&e->p_ws, persist_part_ws_bytes());
+    }
     alloc((void**)&e->xnorm, Mx * c.hidden * 2);
     alloc((void**)&e->xsel, Mx * c.hidden * 2);
     alloc((void**)&e->q, Mx * e->qdim * 2);
@@ -532,7 +591,8 @@ void asd_engine_destroy(asd_engine_t* h) {
     Engine* e = reinterpret_cast<Engine*>(h);
     if (!e) return;
     void* bufs[] = {e->resid, e->part, e->o_part, e->ml_part, e->tickets, e->rope_cs, e->resid_bf, e->sumsq,
-                    e->sumsq_sel, e->tp_buf[0], e->tp_buf[1], e->tp_flags, e->tp_error, e->xnorm, e->xsel, e->q, e->attn, e->act};
+                    e->sumsq_sel, e->tp_buf[0], e->tp_buf[1], e->tp_flags, e->tp_error, e->xnorm, e->xsel, e->q, e->attn, e->act,
+                    e->p_layers, e->p_sync, e->p_ws};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete e;
@@ -556,6 +616,7 @@ int asd_engine_set_layer(asd_engine_t* h, int layer, const void* wqkv, const voi
     if (make_tmap_bf16(&L.t_o, wo, hdn, e->qdim, e->qdim, 128)) return -1;
     if (make_tmap_bf16(&L.t_gu, wgateup, 2 * e->ffp, hdn, hdn, 128)) return -1;
     if (make_tmap_bf16(&L.t_down, wdown, hdn, e->c.ffn, e->c.ffn, 128)) return -1;
+    e->p_layers_ok = false;
     return 0;
 }
 
@@ -581,6 +642,7 @@ int asd_engine_set_kv(asd_engine_t* h, void* kv_pool, int num_pages, const int32
     e->max_pages = max_pages_per_seq;
     e->kv_half = (size_t)num_pages * e->c.n_kv_heads * e->c.page_size * e->c.head_dim;
     e->kv_map_ok = false;
+    e->p_layers_ok = false;
     const unsigned long long rows = 2ull * e->c.n_layers * num_pages * e->c.n_kv_heads * e->c.page_size;
     if (e->c.head_dim == 128 && e->c.page_size == 16 && rows < (1ull << 31)) {
         if (make_tmap_bf16(&e->kv_map, kv_pool, rows, 128, 128, 16)) return -1;
@@ -710,6 +772,8 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "glue_pdl")) e->tune.glue_pdl = value;
     else if (!strcmp(name, "attn_wide")) e->tune.attn_wide = value;
     else if (!strcmp(name, "gemm_big")) e->tune.gemm_big = value;
+    else if (!strcmp(name, "persist")) e->persist = value;
+    else if (!strcmp(name, "persist_ahead")) e->persist_ahead = value;
     else if (!strcmp(name, "fuse_norm")) e->fuse_norm = value;
     else if (!strcmp(name, "early_trigger")) e->tune.gemm_early_trigger = value;
     else if (!strcmp(name, "headroom")) e->tune.gemm_headroom = value;
@@ -729,6 +793,16 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     e->lm_plans.clear();
     e->lm_plans_tc.clear();
     return 0;
+}
+
+// diagnostics: per-CTA globaltimer stamps of the persistent forward kernel (buf: [CTAs][643] u64 on the device;
+// NULL switches tracing off).  Slot 0: kernel entry; slot p + 1: this CTA's share of phase p done (phase 0 embedding,
+// 1 + 5 l + {0 QKV, 1 attention, 2 O, 3 gate|up, 4 down} of layer l, then the logit-row gather and the lm_head).
+int asd_engine_persist_trace(asd_engine_t* h, unsigned long long* buf) {
+    Engine* e = reinterpret_cast<Engine*>(h);
+    if (!e) return set_error("asd_engine_persist_trace: NULL handle");
+    e->p_trace = buf;
+    return persist_num_ctas();
 }
 
 int asd_engine_profile_read(asd_engine_t* h, float* ms_by_class, int* launches_by_class, int nclass) {

@@ -176,7 +176,9 @@ ASD_API int asd_engine_peer_connect(asd_engine_t** engines, int n);
  * "ksplit", "stages" (0 = automatic), "headroom" (shared memory left for the next kernel's CTAs on <= 32-token
  * tiles), "recv_dedicated", "early_trigger", "next_prefetch_mb" (tuning knobs),
  * "tp_fused" (0 never, 1 where it pays, 2 always), "tp_two_shot" (-1 never, 0 where it pays, 1 always), "p2p",
- * "profile" (0/1) */
+ * "persist" (1: single-rank forwards of <= 128 tokens run as ONE cooperative launch of the persistent forward
+ * kernel, forward_persist.cu; 0, default: one launch per GEMM / attention - measured faster),
+ * "persist_ahead" (L2 prefetch distance of the persistent kernel's weight producer, 0 = off), "profile" (0/1) */
 ASD_API int asd_engine_set_option(asd_engine_t* e, const char* name, int value);
 /* With option "profile" = 1 every launch is bracketed by CUDA events on the launching stream;
  * this call synchronises and returns the summed milliseconds and launch counts by kernel class
@@ -190,6 +192,10 @@ ASD_API int asd_debug_gemm_trace(unsigned long long* buf, int max_launches);
 /* Same for the attention kernel: {entry, upstream grid done, metadata read, loads issued, first K/V tile landed,
  * key loop done, key groups merged, partials stored, ticket taken, exit of the merging CTA}. */
 ASD_API int asd_debug_attn_trace(unsigned long long* buf, int max_launches);
+/* Diagnostics of the persistent forward kernel: per-CTA globaltimer stamps into buf (device, u64 [CTAs][643]: slot 0
+ * kernel entry, slot p + 1 = this CTA's share of phase p done; phase 0 embedding, 1 + 5 l + {0 QKV, 1 attention, 2 O,
+ * 3 gate|up, 4 down} of layer l, then logit-row gather and lm_head); returns the number of CTAs; NULL = off. */
+ASD_API int asd_engine_persist_trace(asd_engine_t* e, unsigned long long* buf);
 ASD_API int asd_engine_profile_read(asd_engine_t* e, float* ms_by_class, int* launches_by_class, int nclass);
 /*
  * One forward pass over M tokens (draft step: q_len 1; verify step: q_len k+1; prefill chunk).
