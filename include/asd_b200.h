@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define ASD_B200_ABI_VERSION 1
-#define ASD_NUM_FEATURES 6 /* lse, p_max, margin, entropy, ln p(draft tok), ln p(resampled tok) */
+#define ASD_NUM_FEATURES 6 /* lse, p_max, margin, entropy, ln p(draft tok), ln p(token emitted at this position) */
 
 ASD_API int asd_abi_version(void);
 ASD_API const char* asd_last_error(void);
@@ -49,14 +49,14 @@ ASD_API void asd_reset_launch_count(void);
  *   draft_tokens  i32  [B, k]        u_accept fp64 [B, k]        u_resid fp64 [B]
  *   temperature <= 0 selects greedy verification (accept iff draft token == argmax).
  *   accept_mask u8 [B, k]; accepted_len i32 [B]; out_tokens i32 [B, k+1] (-1 padded);
- *   out_logprobs fp32 [B, k+1] (0 padded); features fp32 [B, k+1, ASD_NUM_FEATURES].
+ *   out_logprobs fp32 [B, k+1] (0 padded); features fp32 [B, k+1, ASD_NUM_FEATURES]; features[.., 5] repeats
+ *   out_logprobs (the residual / bonus draw is only made for the position that emits the new token).
  *   workspace: asd_reject_sample_workspace_bytes(B, k) bytes, zero-filled once before first use.
  * V must be a multiple of 4 and <= 212992; k <= 64; logits 16-byte aligned.  k == 0 samples one
  * token per row from softmax(target/T) (used for the draft model's own sampling).
  */
 ASD_API size_t asd_reject_sample_workspace_bytes(int B, int k);
-/* 1 (default): register-resident kernel with TMA prefetch of the next row when V <= 163840;
- * 0: always the shared-memory-resident kernel (same arithmetic contract, bit-identical results) */
+/* deprecated no-op (round 1 had two kernels behind one arithmetic contract; there is one streaming implementation now) */
 ASD_API void asd_reject_sample_set_impl(int impl);
 ASD_API int asd_reject_sample(const float* target_logits, const float* draft_logits, const int32_t* draft_tokens,
                       const double* u_accept, const double* u_resid, int B, int k, int V, float temperature,

@@ -43,8 +43,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_reject_sample.argtypes = [vp, vp, vp, vp, vp, i, i, i, ctypes.c_float, vp, vp, vp, vp, vp]
         L.oracle_exp2p.restype = ctypes.c_float
         L.oracle_exp2p.argtypes = [ctypes.c_float]
-        L.oracle_cscan_total.restype = ctypes.c_float
-        L.oracle_cscan_total.argtypes = [vp]
+        L.oracle_wsum.restype = ctypes.c_float
+        L.oracle_wsum.argtypes = [vp]
         _LIB = L
     return _LIB
 

@@ -1,43 +1,50 @@
 /*
  * ORACLE (test infrastructure only - never imported by the product path).
  *
- * PARITY UNPINNED: the reference contains no token-level rejection sampler (SURVEY.md
- * section 0 fact 2, section 8c), so there is no reference implementation, test or golden
- * vector to pin this file to.  It restates the canonical speculative-sampling rule the
- * reference cites (docs/papers/FINAL_PAPER.md:22,285):
+ * PARITY UNPINNED against the reference: it contains no token-level rejection sampler (SURVEY.md
+ * section 0 fact 2, section 8c), so there is no reference implementation, test or golden vector
+ * to pin this file to.  It restates the canonical speculative-sampling rule the reference cites
+ * (docs/papers/FINAL_PAPER.md:22,285):
  *     accept x_i  iff  u_i <= min(1, p_i(x_i)/q_i(x_i));
  *     on the first reject resample from normalise(max(0, p - q)); bonus token from p_{k+1};
  * and the reference's only vocab-wide arithmetic, softmax + log(probs[token])
  * (src/training/generate_training_data.py:128-134), for the per-row features.
- * Cross-checked in tests/ against an independent float64 numpy softmax / p-over-q test.
+ * Independent pins: tests/test_oracle_sampler.py (float64 numpy softmax / p-over-q, chi-square of the
+ * resampler) and tests/test_sampler_vllm_gpu.py (the accept rule of the installed vLLM kernels).
  *
- * Because fp32 sums are order dependent, the ARITHMETIC CONTRACT below is part of the
- * definition (SURVEY.md section 7 hard part 2).  The CUDA kernel implements the same
- * contract; this file states it with plain loops:
+ * Because fp32 sums are order dependent, the ARITHMETIC CONTRACT below is part of the definition
+ * (SURVEY.md section 7 hard part 2).  The CUDA kernels (csrc/sampler.cu) implement the same contract;
+ * this file states it with plain loops.  Contract v2 ("chunked streaming": every logit is read from
+ * HBM once by an independent 4096-element chunk, no vocabulary-wide exchange before the exponentials):
  *
- *   c1   = (T > 0) ? (1.0f / T) * LOG2E : LOG2E                       (fp32, rn)
- *   a_v  = z_v * c1                       m1 = max a_v, m2 = second largest (multiset)
- *   t_v  = fmaf(z_v, c1, -m1)             e_v = exp2p(t_v)   (degree-5 polynomial below)
- *   Z    = csum(e_v)                      S  = csum(e_v * t_v)
- *   csum / cscan: element v belongs to lane ((v / 4) mod 4096); a lane adds its
- *     elements in increasing v; the 4096 lane values are then scanned: Hillis-Steele
- *     inside each group of 32 lanes, a sequential chain over the 16 groups of a
- *     512-lane block, a sequential chain over the 8 blocks.  csum = the scan's total.
- *   accept:  (u * (double)eq_x) * (double)Zp  <=  (double)ep_x * (double)Zq    (binary64)
- *   residual weight r_v = max(0, fmaf(ep_v, Zq, -(eq_v * Zp)))   (bonus row: r_v = ep_v)
- *   resample: tau = ur * R (R = cscan total of lane sums of r); pick the first lane whose
- *     inclusive scan value exceeds tau, then the first element inside that lane whose
- *     running sum (started from the previous lane's scan value) exceeds tau.
+ *   c1 = (T > 0) ? (1.0f / T) * LOG2E : LOG2E                              (fp32, rn)
+ *   A row is cut into chunks of 4096 consecutive elements.  Inside chunk c, element with local index u
+ *   belongs to lane ((u / 4) mod 256) and a lane visits its (up to 16) elements in increasing u.
+ *     a_v  = z_v * c1;   m_c = max a_v over the chunk;  (m_c, m2_c) = two largest of the multiset
+ *     t_v  = fmaf(z_v, c1, -m_c);     e_v = exp2p(t_v)      (degree-5 polynomial below)
+ *     lane sums of e_v and of e_v * t_v (left to right from 0), then wsum: Hillis-Steele inclusive scan
+ *     inside each group of 32 lanes, a sequential chain over the 8 groups (its last value is the total).
+ *   Row merge, sequential over the chunks:  M = max m_c;  s_c = exp2p(m_c - M);
+ *     Z = sum_c Z_c * s_c;   S = sum_c fmaf(Z_c, m_c - M, S_c) * s_c;   second maximum by the usual merge.
+ *   A probability is never formed; P_v = e_v * s_c is "p_v * Z".
+ *   accept:  (u * (double)Q_x) * (double)Zp  <=  (double)P_x * (double)Zq                 (binary64)
+ *   Only the row that emits the sequence's new token (the first rejected position, or the bonus row)
+ *   draws from the residual  r_v = max(0, fmaf(P_v, Zq, -(Q_v * Zp)))  (bonus row: r_v = P_v):
+ *     chunk totals R_c by lane sums + wsum, R = sequential sum, tau = ur * R (0 if that is not < R);
+ *     the first chunk whose running total exceeds tau, inside it the first lane whose inclusive scan value
+ *     X + (off_group + hs_lane) exceeds tau (X = running total before the chunk), inside the lane the
+ *     first element whose running sum (started from the previous lane's scan value) exceeds tau.
  */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
-#define LANES 4096
+#define CHUNK 4096
+#define LANES 256
 #define GROUP 32
-#define BLOCK_LANES 512
 #define NFEAT 6
+#define MAXCH 64
 
 static const float LOG2E_F = 0x1.715476p+0f;
 static const float LN2_F = 0x1.62e43p-1f;
@@ -64,15 +71,15 @@ static float exp2p(float t)
     return p;
 }
 
-static int lane_of(int v) { return (v >> 2) & (LANES - 1); }
+static int lane_of(int u) { return (u >> 2) & (LANES - 1); }
 
-/* canonical scan over the 4096 lane values: P inclusive, X = previous lane's P. */
-static float cscan(const float *val, float *P, float *X)
+/* canonical scan of the 256 lane values of a chunk: hs = Hillis-Steele inclusive inside each group of 32,
+ * off[g] = sequential sum of the totals of the groups before g; returns the chunk total. */
+static float wscan(const float *val, float *hs, float *off)
 {
-    static float hs[LANES];
     float tmp[GROUP];
-    float coff = 0.0f;
-    int c, w, i, d;
+    float o = 0.0f;
+    int w, i, d;
     for (w = 0; w < LANES / GROUP; ++w) {
         float *g = hs + w * GROUP;
         memcpy(g, val + w * GROUP, sizeof(float) * GROUP);
@@ -81,97 +88,79 @@ static float cscan(const float *val, float *P, float *X)
             for (i = d; i < GROUP; ++i)
                 g[i] = tmp[i] + tmp[i - d];
         }
+        off[w] = o;
+        o = o + g[GROUP - 1];
     }
-    for (c = 0; c < LANES / BLOCK_LANES; ++c) {
-        float off = 0.0f;
-        for (w = 0; w < BLOCK_LANES / GROUP; ++w) {
-            const float *g = hs + c * BLOCK_LANES + w * GROUP;
-            for (i = 0; i < GROUP; ++i) {
-                float q = off + g[i];
-                P[c * BLOCK_LANES + w * GROUP + i] = coff + q;
-            }
-            off = off + g[GROUP - 1];
-        }
-        coff = coff + off;
-    }
-    if (X) {
-        X[0] = 0.0f;
-        for (i = 1; i < LANES; ++i)
-            X[i] = P[i - 1];
-    }
-    return coff;
+    return o;
+}
+
+static float wsum(const float *val)
+{
+    float hs[LANES], off[LANES / GROUP];
+    return wscan(val, hs, off);
 }
 
 typedef struct {
-    float m1, m2, Z, S;
+    int nc;
+    float m[MAXCH], m2[MAXCH], Z[MAXCH], S[MAXCH], s[MAXCH]; /* per chunk; s = exp2p(m_c - M) */
+    float M, M2, Zt, St;
     int argmax;
-} row_stats_t;
+} row_t;
 
-/* passes 1+2 for one row: e[] and t[] out. */
-static void row_softmax(const float *z, int V, float c1, int want_top2, float *e, float *t,
-                        row_stats_t *st)
+/* chunk statistics + row merge of one row of logits; e[] = chunk-relative exponentials */
+static void row_stats(const float *z, int V, float c1, float *e, row_t *R)
 {
-    static float laneZ[LANES], laneS[LANES], P[LANES];
-    float m1 = -INFINITY, m2 = -INFINITY;
-    int v, amax = 0;
-    for (v = 0; v < V; ++v) {
-        float a = z[v] * c1;
-        if (a > m1) {
-            m2 = m1;
-            m1 = a;
-            amax = v;
-        } else if (a > m2) {
-            m2 = a;
+    int c, v, i;
+    R->nc = (V + CHUNK - 1) / CHUNK;
+    for (c = 0; c < R->nc; ++c) {
+        const int v0 = c * CHUNK, n = (V - v0) < CHUNK ? (V - v0) : CHUNK;
+        float laneZ[LANES], laneS[LANES];
+        float m1 = -INFINITY, m2 = -INFINITY;
+        for (i = 0; i < n; ++i) {
+            float a = z[v0 + i] * c1;
+            if (a > m1) {
+                m2 = m1;
+                m1 = a;
+            } else if (a > m2) {
+                m2 = a;
+            }
         }
+        memset(laneZ, 0, sizeof(laneZ));
+        memset(laneS, 0, sizeof(laneS));
+        for (i = 0; i < n; ++i) {
+            const int l = lane_of(i);
+            const float t = fmaf(z[v0 + i], c1, -m1);
+            const float ex = exp2p(t);
+            e[v0 + i] = ex;
+            laneZ[l] = laneZ[l] + ex;
+            laneS[l] = laneS[l] + ex * t;
+        }
+        R->m[c] = m1;
+        R->m2[c] = m2;
+        R->Z[c] = wsum(laneZ);
+        R->S[c] = wsum(laneS);
     }
-    memset(laneZ, 0, sizeof(laneZ));
-    memset(laneS, 0, sizeof(laneS));
-    for (v = 0; v < V; ++v) {
-        int l = lane_of(v);
-        t[v] = fmaf(z[v], c1, -m1);
-        e[v] = exp2p(t[v]);
-        laneZ[l] = laneZ[l] + e[v];
-        if (want_top2)
-            laneS[l] = laneS[l] + e[v] * t[v];
+    R->M = -INFINITY;
+    R->M2 = -INFINITY;
+    for (c = 0; c < R->nc; ++c) {
+        R->M2 = fmaxf(fminf(R->M, R->m[c]), fmaxf(R->M2, R->m2[c]));
+        R->M = fmaxf(R->M, R->m[c]);
     }
-    st->m1 = m1;
-    st->m2 = m2;
-    st->argmax = amax;
-    st->Z = cscan(laneZ, P, NULL);
-    st->S = want_top2 ? cscan(laneS, P, NULL) : 0.0f;
-}
-
-/* inverse-CDF pick over residual weights r[] in canonical lane order; -1 when R == 0 */
-static int pick(const float *r, int V, float ur)
-{
-    static float laneR[LANES], P[LANES], X[LANES];
-    float R, tau, c;
-    int v, l, sel = -1, last_pos = -1;
-    memset(laneR, 0, sizeof(laneR));
+    R->Zt = 0.0f;
+    R->St = 0.0f;
+    for (c = 0; c < R->nc; ++c) {
+        const float d = R->m[c] - R->M;
+        R->s[c] = exp2p(d);
+        R->Zt = R->Zt + R->Z[c] * R->s[c];
+        R->St = R->St + fmaf(R->Z[c], d, R->S[c]) * R->s[c];
+    }
+    /* arg-max: lowest index attaining the row maximum */
+    R->argmax = 0;
     for (v = 0; v < V; ++v)
-        laneR[lane_of(v)] = laneR[lane_of(v)] + r[v];
-    R = cscan(laneR, P, X);
-    if (!(R > 0.0f))
-        return -1;
-    tau = ur * R;
-    for (l = 0; l < LANES; ++l)
-        if (P[l] > tau && X[l] <= tau)
-            break;
-    if (l == LANES)
-        return -1; /* unreachable: P is monotone and P[last] = R > tau */
-    c = X[l];
-    for (v = 0; v < V; ++v) {
-        if (lane_of(v) != l)
-            continue;
-        if (r[v] > 0.0f)
-            last_pos = v;
-        c = c + r[v];
-        if (c > tau) {
-            sel = v;
+        if (z[v] * c1 == R->M) {
+            R->argmax = v;
             break;
         }
-    }
-    return sel >= 0 ? sel : last_pos;
 }
 
 static float clamp_u(double u)
@@ -184,12 +173,81 @@ static float clamp_u(double u)
     return ur;
 }
 
+/* inverse-CDF draw over the residual weights r[] (already in canonical form); -1 when their total is 0 */
+static int pick(const float *r, int V, float ur)
+{
+    const int nc = (V + CHUNK - 1) / CHUNK;
+    float Rc[MAXCH], lane[LANES], hs[LANES], off[LANES / GROUP];
+    float R = 0.0f, tau, pre = 0.0f, X = 0.0f, cc;
+    int c, i, l, cstar = -1, sel = -1, last_pos = -1, first = -1, lstar = -1;
+    for (c = 0; c < nc; ++c) {
+        const int v0 = c * CHUNK, n = (V - v0) < CHUNK ? (V - v0) : CHUNK;
+        memset(lane, 0, sizeof(lane));
+        for (i = 0; i < n; ++i)
+            lane[lane_of(i)] = lane[lane_of(i)] + r[v0 + i];
+        Rc[c] = wsum(lane);
+        R = R + Rc[c];
+    }
+    if (!(R > 0.0f))
+        return -1;
+    tau = ur * R;
+    if (!(tau < R))
+        tau = 0.0f;
+    for (c = 0; c < nc; ++c) {
+        const float nx = pre + Rc[c];
+        if (nx > tau) {
+            cstar = c;
+            X = pre;
+            break;
+        }
+        pre = nx;
+    }
+    if (cstar < 0)
+        return -1; /* unreachable: the running total ends at R > tau */
+    {
+        const int v0 = cstar * CHUNK, n = (V - v0) < CHUNK ? (V - v0) : CHUNK;
+        float Pprev = 0.0f;
+        memset(lane, 0, sizeof(lane));
+        for (i = 0; i < n; ++i)
+            lane[lane_of(i)] = lane[lane_of(i)] + r[v0 + i];
+        wscan(lane, hs, off);
+        for (l = 0; l < LANES; ++l) {
+            const float P = X + (off[l / GROUP] + hs[l]);
+            /* scan value of the previous lane; for the first lane of a group: X + off (same expression as
+             * the last lane of the previous group) */
+            const float Xl = (l % GROUP == 0) ? X + off[l / GROUP] : Pprev;
+            Pprev = P;
+            if (P > tau) {
+                lstar = l;
+                cc = Xl;
+                break;
+            }
+        }
+        if (lstar < 0)
+            return -1; /* unreachable: the last lane's value equals the running total > tau */
+        for (i = 0; i < n; ++i) {
+            if (lane_of(i) != lstar)
+                continue;
+            if (first < 0)
+                first = v0 + i;
+            if (r[v0 + i] > 0.0f)
+                last_pos = v0 + i;
+            cc = cc + r[v0 + i];
+            if (cc > tau) {
+                sel = v0 + i;
+                break;
+            }
+        }
+    }
+    return sel >= 0 ? sel : (last_pos >= 0 ? last_pos : first);
+}
+
 /*
  * target_logits fp32 [B, k+1, V]; draft_logits fp32 [B, k, V] (NULL allowed when k == 0
  * or temperature <= 0); draft_tokens int32 [B, k]; u_accept fp64 [B, k]; u_resid fp64 [B].
  * Outputs: accept_mask u8 [B, k]; accepted_len i32 [B]; out_tokens i32 [B, k+1] (-1 pad);
  * out_logprobs fp32 [B, k+1] (0 pad); features fp32 [B, k+1, 6] =
- * {lse, p_max, margin p1-p2, entropy, ln p(draft token), ln p(resample candidate)}.
+ * {lse, p_max, margin p1-p2, entropy, ln p(draft token), ln p(token emitted at this position) (0 past it)}.
  * Returns 0, or -1 on bad arguments.
  */
 int oracle_reject_sample(const float *target_logits, const float *draft_logits,
@@ -200,65 +258,52 @@ int oracle_reject_sample(const float *target_logits, const float *draft_logits,
 {
     const int greedy = !(temperature > 0.0f);
     const float c1 = greedy ? LOG2E_F : (1.0f / temperature) * LOG2E_F;
-    float *ep, *tp, *eq, *tq, *r;
+    float *ep, *eq, *r;
     int b, i, v;
-    if (B < 0 || k < 0 || V < 4 || (V & 3))
+    if (B < 0 || k < 0 || k > 64 || V < 4 || (V & 3) || V > CHUNK * MAXCH)
         return -1;
     ep = malloc(sizeof(float) * V);
-    tp = malloc(sizeof(float) * V);
     eq = malloc(sizeof(float) * V);
-    tq = malloc(sizeof(float) * V);
     r = malloc(sizeof(float) * V);
     for (b = 0; b < B; ++b) {
-        int n = 0, rejected = 0;
-        int cand[65];
-        float lp_x[65], lp_y[65];
-        if (k > 64)
-            return -1;
+        int n = 0, rejected = 0, y;
+        int amax[65];
+        float lp_x[65], lp_amax[65], lp_y;
         for (i = 0; i <= k; ++i) {
             const float *zt = target_logits + ((size_t)b * (k + 1) + i) * V;
             const int has_draft = i < k;
             const int x = has_draft ? draft_tokens[b * k + i] : -1;
             const int x_ok = has_draft && x >= 0 && x < V;
-            row_stats_t sp, sq;
+            row_t sp, sq;
             float *f = features + ((size_t)b * (k + 1) + i) * NFEAT;
-            float logZ;
-            int acc = 0, y;
-            row_softmax(zt, V, c1, 1, ep, tp, &sp);
-            logZ = logf(sp.Z);
+            float logZ, log2Z, Px = 0.0f;
+            int acc = 0;
+            row_stats(zt, V, c1, ep, &sp);
+            logZ = logf(sp.Zt);
+            log2Z = log2f(sp.Zt);
+            if (x_ok)
+                Px = ep[x] * sp.s[x / CHUNK];
             if (greedy) {
                 acc = x_ok && x == sp.argmax;
-                y = sp.argmax;
-            } else {
-                if (has_draft) {
-                    const float *zq = draft_logits + ((size_t)b * k + i) * V;
-                    row_softmax(zq, V, c1, 0, eq, tq, &sq);
-                    if (x_ok) {
-                        double lhs = (u_accept[b * k + i] * (double)eq[x]) * (double)sp.Z;
-                        double rhs = (double)ep[x] * (double)sq.Z;
-                        acc = lhs <= rhs;
-                    }
-                    for (v = 0; v < V; ++v) {
-                        float wq = eq[v] * sp.Z;
-                        r[v] = fmaxf(fmaf(ep[v], sq.Z, -wq), 0.0f);
-                    }
-                } else {
-                    for (v = 0; v < V; ++v)
-                        r[v] = ep[v];
-                }
-                y = pick(r, V, clamp_u(u_resid[b]));
-                if (y < 0) /* R == 0: p == q on this row; the draft token itself is a valid draw */
-                    y = x_ok ? x : 0;
+            } else if (has_draft && x_ok) {
+                const float *zq = draft_logits + ((size_t)b * k + i) * V;
+                float Qx;
+                double lhs, rhs;
+                row_stats(zq, V, c1, eq, &sq);
+                Qx = eq[x] * sq.s[x / CHUNK];
+                lhs = (u_accept[b * k + i] * (double)Qx) * (double)sp.Zt;
+                rhs = (double)Px * (double)sq.Zt;
+                acc = lhs <= rhs;
             }
-            f[0] = (sp.m1 + log2f(sp.Z)) * LN2_F;
-            f[1] = 1.0f / sp.Z;
-            f[2] = f[1] - exp2p(sp.m2 - sp.m1) / sp.Z;
-            f[3] = (log2f(sp.Z) - sp.S / sp.Z) * LN2_F;
-            f[4] = x_ok ? logf(ep[x]) - logZ : -INFINITY;
-            f[5] = logf(ep[y]) - logZ;
-            cand[i] = y;
+            f[0] = (sp.M + log2Z) * LN2_F;
+            f[1] = 1.0f / sp.Zt;
+            f[2] = f[1] - exp2p(sp.M2 - sp.M) / sp.Zt;
+            f[3] = (log2Z - sp.St / sp.Zt) * LN2_F;
+            f[4] = x_ok ? logf(Px) - logZ : -INFINITY;
+            f[5] = 0.0f;
+            amax[i] = sp.argmax;
             lp_x[i] = f[4];
-            lp_y[i] = f[5];
+            lp_amax[i] = logf(ep[sp.argmax] * sp.s[sp.argmax / CHUNK]) - logZ;
             if (has_draft) {
                 accept_mask[b * k + i] = (uint8_t)(acc && !rejected);
                 if (acc && !rejected)
@@ -267,20 +312,50 @@ int oracle_reject_sample(const float *target_logits, const float *draft_logits,
                     rejected = 1;
             }
         }
+        /* the emitting row n: arg-max (greedy) or a draw from the residual / the bonus distribution */
+        {
+            const float *zt = target_logits + ((size_t)b * (k + 1) + n) * V;
+            const int has_draft = n < k;
+            const int x = has_draft ? draft_tokens[b * k + n] : -1;
+            const int x_ok = has_draft && x >= 0 && x < V;
+            row_t sp, sq;
+            if (greedy) {
+                y = amax[n];
+                lp_y = lp_amax[n];
+            } else {
+                row_stats(zt, V, c1, ep, &sp);
+                if (has_draft) {
+                    const float *zq = draft_logits + ((size_t)b * k + n) * V;
+                    row_stats(zq, V, c1, eq, &sq);
+                    for (v = 0; v < V; ++v) {
+                        const float P = ep[v] * sp.s[v / CHUNK];
+                        const float Q = eq[v] * sq.s[v / CHUNK];
+                        const float wq = Q * sp.Zt;
+                        r[v] = fmaxf(fmaf(P, sq.Zt, -wq), 0.0f);
+                    }
+                } else {
+                    for (v = 0; v < V; ++v)
+                        r[v] = ep[v] * sp.s[v / CHUNK];
+                }
+                y = pick(r, V, clamp_u(u_resid[b]));
+                if (y < 0) /* residual mass is zero: p == q on this row; the draft token itself is a valid draw */
+                    y = x_ok ? x : 0;
+                lp_y = logf(ep[y] * sp.s[y / CHUNK]) - logf(sp.Zt);
+            }
+        }
         accepted_len[b] = n;
         for (i = 0; i <= k; ++i) {
-            out_tokens[b * (k + 1) + i] = i < n ? draft_tokens[b * k + i] : (i == n ? cand[n] : -1);
-            out_logprobs[b * (k + 1) + i] = i < n ? lp_x[i] : (i == n ? lp_y[n] : 0.0f);
+            out_tokens[b * (k + 1) + i] = i < n ? draft_tokens[b * k + i] : (i == n ? y : -1);
+            out_logprobs[b * (k + 1) + i] = i < n ? lp_x[i] : (i == n ? lp_y : 0.0f);
+            features[((size_t)b * (k + 1) + i) * NFEAT + 5] = out_logprobs[b * (k + 1) + i];
         }
     }
     free(ep);
-    free(tp);
     free(eq);
-    free(tq);
     free(r);
     return 0;
 }
 
 /* exposed for unit tests of the contract pieces */
 float oracle_exp2p(float t) { return exp2p(t); }
-float oracle_cscan_total(const float *lane_vals) { static float P[LANES]; return cscan(lane_vals, P, NULL); }
+float oracle_wsum(const float *lane_vals) { return wsum(lane_vals); }
