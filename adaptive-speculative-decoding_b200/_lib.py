@@ -51,6 +51,9 @@ def lib() -> ctypes.CDLL:
         "asd_stop_rule_host": (i32, [vp, vp, i32, f64, i32, f64, f64, vp]),
         "asd_stop_rule_rows": (i32, [vp, vp, vp, i32, i32, i32, f64, f64, vp, vp, vp]),
         "asd_stop_rule_rows_host": (i32, [vp, vp, vp, i32, i32, i32, f64, f64, vp, vp]),
+        "asd_cascade_decide": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, f64, i32, f64, f64,
+                                     f64, vp, vp, vp, vp]),
+        "asd_engine_persist_trace": (i32, [vp, vp]),
         "asd_engine_peer_connect": (i32, [vp, i32]),
         "asd_bayesian_adjustment_host": (f64, [f64, f64, f64, f64]),
         "asd_linear_bf16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),

@@ -109,6 +109,17 @@ int asd_stop_rule_rows(const double* p, const double* C, const double* lam, int 
     return launch_stop_rule(p, C, n, L, 0.0, risk_adjustment, alpha, beta, k_star, J, static_cast<cudaStream_t>(stream),
                             lam);
 }
+int asd_cascade_decide(const float* features, const int32_t* n_tokens, int n, int T, const double* scalars,
+                       const float* w1, const float* b1, const float* w2, const float* b2, int feature_dim,
+                       const double* prev_p, const double* C, int L, int stage_idx, int prefix_mode, double lam,
+                       int risk_adjustment, double n_obs, double alpha, double beta, double* prob, int32_t* stop,
+                       int32_t* k_star, void* stream) {
+    if (!features || !n_tokens || !scalars || !w1 || !b1 || !w2 || !b2 || !prev_p || !C || !prob || !stop || !k_star)
+        return set_error("asd_cascade_decide: NULL argument");
+    return launch_cascade_decide(features, n_tokens, n, T, scalars, w1, b1, w2, b2, feature_dim, prev_p, C, L, stage_idx,
+                                 prefix_mode, lam, risk_adjustment, n_obs, alpha, beta, prob, stop, k_star,
+                                 static_cast<cudaStream_t>(stream));
+}
 int asd_stop_rule_rows_host(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
                             double alpha, double beta, int32_t* k_star, double* J) {
     return stop_rule_rows_host(p, C, lam, n, L, risk_adjustment, alpha, beta, k_star, J);

@@ -82,6 +82,10 @@ extern int g_sampler_impl;
 // stop_rule.cu
 int launch_stop_rule(const double* p, const double* C, int n, int L, double lam, int risk_adjustment, double alpha,
                      double beta, int* k_star, double* J, cudaStream_t stream, const double* lam_rows = nullptr);
+int launch_cascade_decide(const float* features, const int* n_tokens, int n, int T, const double* scalars, const float* w1,
+                          const float* b1, const float* w2, const float* b2, int fdim, const double* prev_p,
+                          const double* C, int L, int stage_idx, int mode, double lam, int risk, double n_obs,
+                          double alpha, double beta, double* prob, int* stop, int* k_star, cudaStream_t stream);
 int stop_rule_rows_host(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
                         double alpha, double beta, int* k_star, double* J);
 int stop_rule_host(const double* p, const double* C, int L, double lam, int risk_adjustment, double alpha,

@@ -3,8 +3,9 @@
 // in front of the exponentials.
 //
 //   sampler_stats_kernel   grid = rows x chunks (a chunk = 4096 consecutive logits of one row, the draft row's
-//     chunk next to the target's), 256 threads, 16 + 16 logits per thread in registers (128-bit coalesced
-//     loads, streaming cache policy).  Per chunk: maxima (warp shuffles + one shared-memory hop), exponentials
+//     chunk next to the target's), 256 threads; the chunk pair lands in shared memory through two 1-D bulk (TMA)
+//     copies, so no register holds data in flight: 40 registers, 6 CTAs = 48 warps and 192 KB of loads per SM.
+//     Per chunk: maxima (warp shuffles + one shared-memory hop), exponentials
 //     relative to the CHUNK maximum (polynomial exp2 on the packed fp32x2 pipe), lane sums and the canonical
 //     warp scan; one 32-byte record per (row, chunk).  The last CTA of a row to finish (atomic ticket) merges the
 //     row's records (rescaling by 2^(m_c - M)), runs the min(1, p/q) accept test in binary64 and writes the
@@ -12,7 +13,8 @@
 //   sampler_draw_kernel    grid = sequences x chunks, only for the ONE row per sequence that emits a new token (first
 //     rejected position or bonus row): residual max(0, p - q) chunk totals, then the last CTA of the sequence walks
 //     the chunk totals, re-reads the selected chunk (L2) and finishes the inverse-CDF draw inside it.  Launched
-//     programmatically behind the first kernel; not launched at all for greedy verification.
+//     programmatically behind the first kernel and gated per sequence by a flag, so it overlaps the first kernel's
+//     tail; not launched at all for greedy verification.
 // DRAM traffic = (1 + ~1/(k+1)) x the algorithmic bytes.  The previous design (a cluster of 8 CTAs holding a row
 // pair on chip through three dependent cluster-wide exchanges, round 1) read every byte exactly once but ran at
 // 0.15-0.19 of HBM speed: one row pair occupied 8 SMs for ~15 us of barrier latency.
@@ -47,7 +49,7 @@ struct SamplerParams {
     const int* draft_tokens;   // [B, k]
     const double* u_accept;    // [B, k]
     const double* u_resid;     // [B]
-    int B, k, V, NC, greedy;
+    int B, k, V, NC, greedy, flags;   // flags: 4 = the draw kernel is gated per sequence (no grid-wide wait), 8 = acq_rel ticket
     float c1;
     // outputs
     uint8_t* accept_mask;
@@ -103,6 +105,12 @@ __device__ __forceinline__ float2 exp2p2(float2 t) {
                        __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23)));
 }
 
+__device__ __forceinline__ int atom_add_release(int* p, int v) {
+    int old;
+    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 // Hillis-Steele inclusive scan inside the warp (the contract's order)
 __device__ __forceinline__ float warp_hs(float x, int lane) {
 #pragma unroll
@@ -122,53 +130,65 @@ __device__ __forceinline__ void exp4(float4& z, float2 c1v, float2 nmv, float2& 
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 1
-__global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerParams p) {
-    __shared__ float s_red[kSW][4];
+// The chunk (16 KB target + 16 KB draft) lands in shared memory through two 1-D bulk (TMA) copies, so no register
+// holds data in flight: 42 registers per thread, 6 CTAs = 48 warps per SM, up to 192 KB of loads in flight per SM.
+__global__ void __launch_bounds__(kST, 6) sampler_stats_kernel(const SamplerParams p) {
+    __shared__ __align__(128) float4 s_zt[kChunk / 4];
+    __shared__ __align__(128) float4 s_zq[kChunk / 4];
+    __shared__ __align__(16) float4 s_recp[kMaxChunks], s_recq[kMaxChunks];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_red[kSW][4], s_red2[kSW][4];
     __shared__ unsigned long long s_key[kSW];
-    __shared__ float4 s_recp[kMaxChunks], s_recq[kMaxChunks];
     __shared__ int s_last;
     grid_dep_launch();      // the draw kernel may be scheduled; it waits for this grid before reading anything
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k1 = p.k + 1, V = p.V, NC = p.NC;
-    const int row = blockIdx.x / NC, c = blockIdx.x - row * NC;
-    const int b = row / k1, i = row - b * k1;
-    const bool has_draft = (i < p.k) && !p.greedy;
+    const int total = p.B * k1 * NC;
     const float c1 = p.c1;
     const float2 c1v = make_float2(c1, c1);
-    const int n4 = min(kChunk / 4, (V - c * kChunk) >> 2);     // float4s of this chunk that exist
-
-    // ---- load: 4 (+4) coalesced 16-byte loads per thread, all in flight together
-    const float4* zt_g = reinterpret_cast<const float4*>(p.target + (size_t)row * V + (size_t)c * kChunk);
-    const float4* zq_g =
-        has_draft ? reinterpret_cast<const float4*>(p.draft + ((size_t)b * p.k + i) * V + (size_t)c * kChunk) : nullptr;
-    float4 zt[kSlots], zq[kSlots];
-    bool have[kSlots];
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-        have[s] = s * kST + tid < n4;
-        zt[s] = have[s] ? __ldcs(zt_g + s * kST + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // thread 0: bulk copies of one (row, chunk) item into the chunk buffers
+    auto issue = [&](int item) {
+        const int row = item / NC, c = item - row * NC;
+        const int b = row / k1, i = row - b * k1;
+        const bool hd = (i < p.k) && !p.greedy;
+        const uint32_t bytes = (uint32_t)min(kChunk / 4, (V - c * kChunk) >> 2) * 16u;
+        mbar_expect_tx(&s_bar, hd ? 2 * bytes : bytes);
+        bulk_g2s(s_zt, p.target + (size_t)row * V + (size_t)c * kChunk, bytes, &s_bar);
+        if (hd) bulk_g2s(s_zq, p.draft + ((size_t)b * p.k + i) * V + (size_t)c * kChunk, bytes, &s_bar);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        issue(blockIdx.x);
     }
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s)
-        zq[s] = (has_draft && have[s]) ? __ldcs(zq_g + s * kST + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();            // the barrier is initialised
+    uint32_t phase = 0;
+    // Persistent CTAs, items dealt round-robin: the bulk copies of a CTA's NEXT item are issued as soon as every thread
+    // has consumed the current chunk, so they fly while thread 0 finishes the chunk (sums, record, fence, ticket).
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int row = item / NC, c = item - row * NC;
+    const int b = row / k1, i = row - b * k1;
+    const bool has_draft = (i < p.k) && !p.greedy;
+    const int n4 = min(kChunk / 4, (V - c * kChunk) >> 2);     // float4s of this chunk that exist
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
 
-    // ---- chunk maxima (exact, order independent)
+    // ---- chunk maxima on the raw logits: rn multiplication by c1 > 0 is monotone, so the two largest a = z * c1 of
+    // the multiset are the products of the two largest z (exact, order independent)
     float m1 = -INFINITY, m2 = -INFINITY, mq = -INFINITY;
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-        if (have[s]) {
-            const float2 a0 = __fmul2_rn(make_float2(zt[s].x, zt[s].y), c1v);
-            const float2 a1 = __fmul2_rn(make_float2(zt[s].z, zt[s].w), c1v);
-            const float a[4] = {a0.x, a0.y, a1.x, a1.y};
+        if (s * kST + tid < n4) {
+            const float4 z = s_zt[s * kST + tid];
+            const float a[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 m2 = fmaxf(m2, fminf(m1, a[e]));
                 m1 = fmaxf(m1, a[e]);
             }
             if (has_draft) {
-                const float2 q0 = __fmul2_rn(make_float2(zq[s].x, zq[s].y), c1v);
-                const float2 q1 = __fmul2_rn(make_float2(zq[s].z, zq[s].w), c1v);
-                mq = fmaxf(mq, fmaxf(fmaxf(q0.x, q0.y), fmaxf(q1.x, q1.y)));
+                const float4 q = s_zq[s * kST + tid];
+                mq = fmaxf(mq, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
             }
         }
     }
@@ -193,24 +213,27 @@ __global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerPara
         m1 = fmaxf(m1, o1);
         mq = fmaxf(mq, s_red[w][2]);
     }
+    m1 = __fmul_rn(m1, c1);
+    m2 = __fmul_rn(m2, c1);
+    mq = __fmul_rn(mq, c1);
 
-    // ---- exponentials relative to the chunk maximum, lane sums in increasing element order
-    float zs = 0.0f, ss = 0.0f, qs = 0.0f;
+    // ---- exponentials relative to the chunk maximum; a lane keeps two running sums (elements with even / odd local
+    // index, each left to right) on the packed fp32x2 pipe and adds them at the end
+    float2 zs2 = make_float2(0.f, 0.f), ss2 = zs2, qs2 = zs2;
     unsigned long long key = ~0ull;                      // greedy: (lowest index attaining the maximum, its e)
     const float2 nm1v = make_float2(-m1, -m1), nmqv = make_float2(-mq, -mq);
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-        if (have[s]) {
-            const float4 zraw = zt[s];
+        if (s * kST + tid < n4) {
+            float4 z = s_zt[s * kST + tid];
+            const float4 zraw = z;
             float2 t0, t1;
-            exp4(zt[s], c1v, nm1v, t0, t1);
-            const float2 w0 = __fmul2_rn(make_float2(zt[s].x, zt[s].y), t0);
-            const float2 w1 = __fmul2_rn(make_float2(zt[s].z, zt[s].w), t1);
-            zs = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(zs, zt[s].x), zt[s].y), zt[s].z), zt[s].w);
-            ss = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(ss, w0.x), w0.y), w1.x), w1.y);
+            exp4(z, c1v, nm1v, t0, t1);
+            zs2 = __fadd2_rn(__fadd2_rn(zs2, make_float2(z.x, z.y)), make_float2(z.z, z.w));
+            ss2 = __fadd2_rn(__fadd2_rn(ss2, __fmul2_rn(make_float2(z.x, z.y), t0)), __fmul2_rn(make_float2(z.z, z.w), t1));
             if (p.greedy) {
                 const float zz[4] = {zraw.x, zraw.y, zraw.z, zraw.w};
-                const float ee[4] = {zt[s].x, zt[s].y, zt[s].z, zt[s].w};
+                const float ee[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if (__fmul_rn(zz[e], c1) == m1) {
@@ -220,31 +243,21 @@ __global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerPara
                     }
             }
             if (has_draft) {
+                float4 q = s_zq[s * kST + tid];
                 float2 u0, u1;
-                exp4(zq[s], c1v, nmqv, u0, u1);
-                qs = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(qs, zq[s].x), zq[s].y), zq[s].z), zq[s].w);
+                exp4(q, c1v, nmqv, u0, u1);
+                qs2 = __fadd2_rn(__fadd2_rn(qs2, make_float2(q.x, q.y)), make_float2(q.z, q.w));
             }
         }
     }
-    // ---- the draft token's exponentials (the thread that holds it reports them)
+    const float zs = __fadd_rn(zs2.x, zs2.y), ss = __fadd_rn(ss2.x, ss2.y), qs = __fadd_rn(qs2.x, qs2.y);
+    // ---- the draft token's exponentials (one thread recomputes them from the chunk in shared memory)
     const int x = (i < p.k) ? p.draft_tokens[b * p.k + i] : -1;
     const bool x_ok = (i < p.k) && x >= 0 && x < V;
-    if (x_ok && x / kChunk == c) {
-        const int u = x - c * kChunk, j = u >> 2;
-        if ((j & (kST - 1)) == tid) {
-            const int sx = j / kST;
-            float epx = 0.f, eqx = 0.f;
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s)
-                if (s == sx) {
-                    const float pe[4] = {zt[s].x, zt[s].y, zt[s].z, zt[s].w};
-                    const float qe[4] = {zq[s].x, zq[s].y, zq[s].z, zq[s].w};
-                    epx = pe[u & 3];
-                    eqx = qe[u & 3];
-                }
-            p.row_px[row] = epx;
-            p.row_qx[row] = eqx;
-        }
+    if (tid == 32 && x_ok && x / kChunk == c) {
+        const int u = x - c * kChunk;
+        p.row_px[row] = exp2p(__fmaf_rn(reinterpret_cast<const float*>(s_zt)[u], c1, -m1));
+        if (has_draft) p.row_qx[row] = exp2p(__fmaf_rn(reinterpret_cast<const float*>(s_zq)[u], c1, -mq));
     }
     // ---- canonical chunk totals: Hillis-Steele inside the warp, sequential chain over the 8 warps
     const float hz = warp_hs(zs, lane), hs_ = warp_hs(ss, lane), hq = warp_hs(qs, lane);
@@ -255,31 +268,36 @@ __global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerPara
             key = o < key ? o : key;
         }
     }
-    __syncthreads();     // s_red is rewritten
     if (lane == 31) {
-        s_red[warp][0] = hz;
-        s_red[warp][1] = hs_;
-        s_red[warp][2] = hq;
+        s_red2[warp][0] = hz;
+        s_red2[warp][1] = hs_;
+        s_red2[warp][2] = hq;
     }
     if (lane == 0) s_key[warp] = key;
-    __syncthreads();
+    __syncthreads();            // every thread is done with the chunk buffers
     if (tid == 0) {
+        fence_proxy_async_smem();   // generic reads of the buffers ordered before the async-proxy writes of the next copy
+        if (item + (int)gridDim.x < total) issue(item + gridDim.x);
         float Z = 0.0f, S = 0.0f, Zq = 0.0f;
         unsigned long long kk = ~0ull;
         for (int w = 0; w < kSW; ++w) {
-            Z = __fadd_rn(Z, s_red[w][0]);
-            S = __fadd_rn(S, s_red[w][1]);
-            Zq = __fadd_rn(Zq, s_red[w][2]);
+            Z = __fadd_rn(Z, s_red2[w][0]);
+            S = __fadd_rn(S, s_red2[w][1]);
+            Zq = __fadd_rn(Zq, s_red2[w][2]);
             kk = s_key[w] < kk ? s_key[w] : kk;
         }
         __stcg(&p.rec_p[(size_t)row * NC + c], make_float4(m1, m2, Z, S));
         __stcg(&p.rec_q[(size_t)row * NC + c],
                make_float4(mq, Zq, __uint_as_float((unsigned)(kk & 0xffffffffu)), __int_as_float((int)(kk >> 32))));
-        __threadfence();
-        s_last = atomicAdd(&p.row_ticket[row], 1) == NC - 1;
+        if (p.flags & 8) {
+            s_last = atom_add_release(&p.row_ticket[row], 1) == NC - 1;   // orders the record stores before the ticket
+        } else {
+            __threadfence();
+            s_last = atomicAdd(&p.row_ticket[row], 1) == NC - 1;
+        }
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) continue;
 
     // ================================================================ last CTA of the row: merge its chunk records
     __threadfence();
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerPara
         s_recq[tid] = __ldcg(&p.rec_q[(size_t)row * NC + tid]);
     }
     __syncthreads();
-    if (tid != 0) return;
+    if (tid != 0) continue;
     float M = -INFINITY, M2 = -INFINITY, Mq = -INFINITY;
     for (int c2 = 0; c2 < NC; ++c2) {
         M2 = fmaxf(fminf(M, s_recp[c2].x), fmaxf(M2, s_recp[c2].y));
@@ -340,7 +358,7 @@ __global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerPara
     }
     p.row_ticket[row] = 0;
     __threadfence();
-    if (atomicAdd(&p.seq_ticket[b], 1) != p.k) return;
+    if (atomicAdd(&p.seq_ticket[b], 1) != p.k) continue;
     // ================================================================ last row of the sequence: first-reject prefix
     __threadfence();
     int n = 0;
@@ -362,8 +380,14 @@ __global__ void __launch_bounds__(kST, 4) sampler_stats_kernel(const SamplerPara
         p.out_logprobs[b * k1 + t] = lp;
         p.features[(size_t)(b * k1 + t) * kNFeat + 5] = lp;
     }
-    p.need_row[b] = n;
     p.seq_ticket[b] = 0;
+    if (!p.greedy) {
+        // release: everything the draw kernel reads for this sequence (records, row statistics: written by other CTAs
+        // and observed here through the tickets) is ordered before the flag
+        __threadfence();
+        *reinterpret_cast<volatile int*>(&p.need_row[b]) = n + 1;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel 2
@@ -423,11 +447,24 @@ __global__ void __launch_bounds__(kST, 4) sampler_draw_kernel(const SamplerParam
     __shared__ float s_rc[kMaxChunks];
     __shared__ int s_flag, s_cstar, s_tstar[kSW];
     __shared__ float s_tau, s_X;
-    grid_dep_wait();        // everything below depends on the statistics kernel
+    // Launched programmatically: these CTAs become resident while the statistics kernel drains its last wave and wait
+    // for THEIR sequence only (flag = emitting position + 1, set by the sequence's finaliser with release semantics),
+    // so the draws of the early sequences overlap the statistics of the late ones.  No deadlock: this grid is only
+    // scheduled once every CTA of the statistics kernel has started, and those never wait for anything.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k1 = p.k + 1, NC = p.NC;
     const int b = blockIdx.x / NC, c = blockIdx.x - b * NC;
-    const int n = __ldcg(&p.need_row[b]);
+    if (!(p.flags & 4)) grid_dep_wait();
+    if (tid == 0) {
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.need_row + b) : "memory");
+        } while (v == 0);
+        s_cstar = v - 1;
+    }
+    __syncthreads();
+    const int n = s_cstar;
+    __syncthreads();
     const int row = b * k1 + n;
     const bool has_draft = n < p.k;
     const float4 st = __ldcg(&p.row_stat[row]);
@@ -477,6 +514,7 @@ __global__ void __launch_bounds__(kST, 4) sampler_draw_kernel(const SamplerParam
         s_tau = tau;
         s_X = X;
         p.seq_ticket2[b] = 0;
+        p.need_row[b] = 0;          // every CTA of this sequence has read the flag (they ticket after reading it)
     }
     __syncthreads();
     const int cstar = s_cstar;
@@ -551,7 +589,9 @@ __global__ void __launch_bounds__(kST, 4) sampler_draw_kernel(const SamplerParam
     p.features[(size_t)row * kNFeat + 5] = lp;
 }
 
-int g_sampler_impl = 1;   // kept for ABI compatibility (asd_reject_sample_set_impl): there is one implementation now
+// asd_reject_sample_set_impl bit flags: 2 = persistent statistics CTAs (experiment, slower), 4 = draw kernel gated per
+// sequence instead of the grid-wide wait (default: +4-7 % at B*k >= 512), 8 = single acq_rel ticket atomic (no gain)
+int g_sampler_impl = 5;
 
 static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -595,6 +635,7 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
     p.V = V;
     p.NC = NC;
     p.greedy = greedy;
+    p.flags = g_sampler_impl;
     p.c1 = greedy ? 0x1.715476p+0f : (1.0f / temperature) * 0x1.715476p+0f;
     p.accept_mask = accept_mask;
     p.accepted_len = accepted_len;
@@ -623,7 +664,16 @@ int launch_reject_sample(const float* target, const float* draft, const int* dra
     p.row_lpamax = reinterpret_cast<float*>(take(sizeof(float) * rows));
     p.seq_rc = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * kMaxChunks));
 
-    sampler_stats_kernel<<<dim3((unsigned)(rows * NC)), kST, 0, stream>>>(p);
+    static int sms[64];
+    int dev = 0;
+    ASD_CUDA(cudaGetDevice(&dev));
+    if (sms[dev & 63] == 0) ASD_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    // One CTA per item by default.  impl 2 (asd_reject_sample_set_impl, experiments): persistent CTAs that prefetch
+    // their next item - measured 2.5x SLOWER on B200 (18 us per item and CTA), so the hardware block scheduler keeps
+    // the job of refilling SM slots.
+    const size_t items = rows * NC, resident = (size_t)6 * sms[dev & 63];
+    const size_t grid = (g_sampler_impl == 2 && items > resident) ? resident : items;
+    sampler_stats_kernel<<<dim3((unsigned)grid), kST, 0, stream>>>(p);
     ASD_CUDA(cudaGetLastError());
     count_launch(1);
     if (!greedy) {

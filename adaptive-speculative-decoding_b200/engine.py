@@ -628,8 +628,9 @@ class SpecDecoder:
                     done = int(f0.item()) >= max_new_tokens
             torch.cuda.current_stream().synchronize()
             n = max_new_tokens
-            res = (toks[:, :n].cpu(), lps[:, :n].cpu(), feats[:, :n].cpu(),
-                   {"accepted": int(accepted.item()), "steps": steps})
+            feats_dev = feats[:, :n].contiguous()      # stays on the device for asd_cascade_decide (scorer -> stop rule)
+            res = (toks[:, :n].cpu(), lps[:, :n].cpu(), feats_dev.cpu(),
+                   {"accepted": int(accepted.item()), "steps": steps, "features_device": feats_dev})
         for e in (self.t, self.d):
             if e is not None and getattr(e, "tp_size", 1) > 1 and e.tp_error():
                 raise AsdError("tensor-parallel peer did not answer within the spin bound (asd_engine_tp_error)")

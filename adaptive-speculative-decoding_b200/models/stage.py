@@ -41,12 +41,14 @@ class FusedLogprobs(np.ndarray):
     (lse, p_max, margin, entropy, ln p(draft tok), ln p(emitted tok)) computed by the sampling kernel over
     the FULL vocabulary (asd_b200.ops.FEATURE_NAMES)."""
     fused: Optional[np.ndarray] = None
+    fused_device = None     # the same [T, 6] rows as a CUDA tensor (input of asd_cascade_decide; never copied back)
 
     def __array_finalize__(self, obj):
         self.fused = getattr(obj, "fused", None)
+        self.fused_device = getattr(obj, "fused_device", None)
 
 
-def make_logprobs(emitted_lp: np.ndarray, fused: np.ndarray) -> FusedLogprobs:
+def make_logprobs(emitted_lp: np.ndarray, fused: np.ndarray, fused_device=None) -> FusedLogprobs:
     T = len(emitted_lp)
     a = np.full((T, 5), PAD_LOGPROB, dtype=np.float64)
     if T:
@@ -55,6 +57,7 @@ def make_logprobs(emitted_lp: np.ndarray, fused: np.ndarray) -> FusedLogprobs:
         a[:, 0], a[:, 1], a[:, 2] = emitted_lp, np.log(pmax), np.log(p2)
     out = a.view(FusedLogprobs)
     out.fused = np.asarray(fused, dtype=np.float32)
+    out.fused_device = fused_device
     return out
 
 
@@ -235,15 +238,39 @@ class Stage:
                 toks, lp, fused, st = self._generate_ids([ids[i] for i in grp], max_tokens, temperature)
                 acc_tok += st["accepted"]
                 steps += st["steps"]
+                fdev = st.get("features_device")
                 for j, i in enumerate(grp):
                     texts[i] = self.tokenizer.decode(toks[j])
-                    lps[i] = make_logprobs(lp[j], fused[j]) if return_logprobs else np.array([])
+                    lps[i] = (make_logprobs(lp[j], fused[j], None if fdev is None else fdev[j])
+                              if return_logprobs else np.array([]))
         finally:
             for st in reversed(chain):
                 st._lock.release()
         stats = {"generation_time_ms": (time.time() - t0) * 1000.0, "draft_tokens_accepted": acc_tok,
                  "decode_steps": steps}
         return texts, lps, stats
+
+    def decide(self, predictor, prompts: List[str], outputs: List[str], logprobs, prev_probs, costs, stage_idx: int,
+               lam: float, prefix_mode: bool = False, risk_adjustment: bool = False, n_obs: float = 100.0,
+               alpha: float = 1.0, beta: float = 1.0):
+        """Scorer -> stop decision for requests that just ran this stage, on the device (``asd_cascade_decide``):
+        the per-token features of ``logprobs[i].fused_device`` never leave the GPU; returns
+        (prob [n], stop [n], k_star [n]) as numpy.  Same chain as pipeline.py:225-256 of the reference."""
+        import torch
+        from ..ops import cascade_decide
+        rows = [lp.fused_device for lp in logprobs]
+        T = max(int(r.shape[0]) for r in rows)
+        dev = rows[0].device
+        if len(rows) == 1 and rows[0].is_contiguous():
+            feats = rows[0][None]
+        else:
+            feats = torch.zeros(len(rows), T, rows[0].shape[1], dtype=torch.float32, device=dev)
+            for i, r in enumerate(rows):
+                feats[i, :r.shape[0]] = r
+        ntok = torch.tensor([int(r.shape[0]) for r in rows], dtype=torch.int32).to(dev, non_blocking=True)
+        scalars = [[len(p.split()) / 2048, len(o.split()) / 512, stage_idx / 4.0] for p, o in zip(prompts, outputs)]
+        return cascade_decide(feats, ntok, scalars, predictor, prev_probs, costs, stage_idx, lam, prefix_mode,
+                              risk_adjustment, n_obs, alpha, beta)
 
     def get_model_info(self) -> Dict[str, object]:
         return {"model_name": self.model_name, "model_size": self.model_size, "parameters": self.cfg.params,

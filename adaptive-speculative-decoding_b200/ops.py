@@ -148,3 +148,50 @@ def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor
     u = torch.zeros(ffp, K, dtype=up_w.dtype, device=up_w.device)
     g[:ff], u[:ff] = gate_w, up_w
     return torch.stack([g.view(ffp // 64, 64, K), u.view(ffp // 64, 64, K)], dim=1).reshape(2 * ffp, K).contiguous()
+
+
+def cascade_decide(features: torch.Tensor, n_tokens: torch.Tensor, scalars, predictor, prev_p, costs, stage_idx: int,
+                   lam: float, prefix_mode: bool = False, risk_adjustment: bool = False, n_obs: float = 100.0,
+                   alpha: float = 1.0, beta: float = 1.0):
+    """Scorer -> stop decision on the device through ``asd_cascade_decide``.
+
+    features fp32 CUDA [n, T, 6] (the sampler's per-token rows, never copied to the host), n_tokens int32 CUDA [n];
+    scalars [n, 3] (prompt words / 2048, output words / 512, stage / 4); predictor: a ``QualityPredictor`` (its MLP
+    weights are uploaded once per device and cached on the module); prev_p [n, stage_idx] acceptance probabilities of
+    the earlier stages; costs [L].  Returns numpy (prob float64 [n], stop bool [n], k_star int32 [n]) - the only
+    device-to-host traffic of the decision."""
+    import numpy as np
+    if not features.is_cuda:
+        raise AsdError("asd_cascade_decide needs CUDA tensors (no CPU fallback)")
+    dev = features.device
+    n, T, F = features.shape
+    assert F == NUM_FEATURES and features.dtype == torch.float32 and features.is_contiguous()
+    assert n_tokens.dtype == torch.int32 and n_tokens.numel() == n and n_tokens.device == dev
+    L = len(costs)
+    cache = getattr(predictor, "_asd_device_weights", None)
+    if cache is None:
+        cache = predictor._asd_device_weights = {}
+    key = (str(dev), predictor.mlp[0].weight._version, predictor.mlp[3].weight._version)
+    if key not in cache:
+        cache.clear()
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        cache[key] = (f32(predictor.mlp[0].weight), f32(predictor.mlp[0].bias), f32(predictor.mlp[3].weight).view(-1),
+                      f32(predictor.mlp[3].bias))
+    w1, b1, w2, b2 = cache[key]
+    pp = np.ones((n, L), np.float64)
+    if stage_idx > 0:
+        pp[:, :stage_idx] = np.asarray(prev_p, dtype=np.float64).reshape(n, stage_idx)
+    host = torch.from_numpy(np.concatenate([np.asarray(scalars, np.float64).reshape(n * 3), pp.reshape(-1),
+                                            np.asarray(costs, np.float64)]))
+    d = host.to(dev, non_blocking=True)
+    sc, pv, C = d[:n * 3], d[n * 3:n * 3 + n * L], d[n * 3 + n * L:]
+    prob = torch.empty(n, dtype=torch.float64, device=dev)
+    out = torch.empty(2, n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib().asd_cascade_decide(features.data_ptr(), n_tokens.data_ptr(), n, T, sc.data_ptr(), w1.data_ptr(),
+                                      b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w1.shape[1], pv.data_ptr(), C.data_ptr(),
+                                      L, int(stage_idx), int(bool(prefix_mode)), float(lam), int(bool(risk_adjustment)),
+                                      float(n_obs), float(alpha), float(beta), prob.data_ptr(), out[0].data_ptr(),
+                                      out[1].data_ptr(), _stream())
+    check(rc, "asd_cascade_decide")
+    return prob.cpu().numpy(), out[0].cpu().numpy().astype(bool), out[1].cpu().numpy()

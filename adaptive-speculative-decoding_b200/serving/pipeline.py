@@ -48,6 +48,8 @@ class PipelineConfig:
     # additions (not in the reference)
     stage_names: Optional[List[str]] = None
     reference_compat: bool = False
+    # scorer -> stop decision on the GPU (asd_cascade_decide) whenever the stage returned device-resident features
+    device_policy: bool = True
 
 
 @dataclass
@@ -151,6 +153,24 @@ class AdaptiveSpeculativePipeline:
         k_full, _ = optimal_stopping_rule(p=full_p, C=all_costs, lam=self.config.lambda_value, risk_adjustment=False)
         return k_full <= stage_idx, stage_idx
 
+    def _device_decide(self, stage, prompts, outputs, logprobs, prev_probs, costs, all_costs, stage_idx, n_stages, n_obs):
+        """(prob, stop, k_star) arrays from ``Stage.decide`` (one ``asd_cascade_decide`` launch for all requests), or
+        None when the stage is not a B200 stage / returned no device features / the predictor is not the MLP."""
+        if not self.config.device_policy or not hasattr(stage, "decide"):
+            return None
+        if any(getattr(lp, "fused_device", None) is None for lp in logprobs):
+            return None
+        mlp = getattr(self.predictor, "mlp", None)
+        if mlp is None or len(mlp) < 4 or type(self.feature_extractor).__name__ != "FeatureExtractor":
+            return None
+        compat = self.config.reference_compat
+        C = list(costs[:stage_idx + 1]) if compat else list(all_costs)
+        if compat:
+            C = C + [0.0] * (n_stages - len(C))       # only the first stage_idx + 1 entries are read in prefix mode
+        return stage.decide(self.predictor, prompts, outputs, logprobs, prev_probs, C, stage_idx,
+                            self.config.lambda_value, prefix_mode=compat, risk_adjustment=self.config.risk_adjustment,
+                            n_obs=n_obs, alpha=self.config.risk_alpha, beta=self.config.risk_beta)
+
     # -- pipeline.py:165-286
     def _process_stages(self, request_id: str, prompt: str, max_tokens: int, temperature: float,
                         start_time: float) -> RequestResult:
@@ -183,17 +203,24 @@ class AdaptiveSpeculativePipeline:
             outputs.append(stage_output[0])
             costs.append(stage.cost_per_token)
             total_tokens += len(stage_output[0].split())
-            if stage_idx < len(stage_names) - 1:
-                prob = self.predictor.predict(prompt=current_prompt, draft_output=stage_output[0],
-                                              draft_logprobs=stage_logprobs[0] if len(stage_logprobs) else None,
-                                              stage_id=stage_idx, feature_extractor=self.feature_extractor)
-                if self.config.risk_adjustment:
-                    n_obs = max(100, self.stats["total_requests"])                       # :235
-                    prob = bayesian_adjustment(prob, n_obs, self.config.risk_alpha, self.config.risk_beta)
-                probabilities.append(prob)
+            dev = self._device_decide(stage, [current_prompt], [stage_output[0]],
+                                      [stage_logprobs[0]] if len(stage_logprobs) else [None], [probabilities], costs,
+                                      all_costs, stage_idx, len(stage_names), max(100, self.stats["total_requests"]))
+            if dev is not None:      # features -> MLP -> shrinkage -> DP in one launch on the GPU
+                probabilities.append(float(dev[0][0]))
+                stop, k_star = bool(dev[1][0]), int(dev[2][0])
             else:
-                probabilities.append(1.0)                                                # :241-242
-            stop, k_star = self._decide(probabilities, costs, stage_idx, len(stage_names), all_costs)
+                if stage_idx < len(stage_names) - 1:
+                    prob = self.predictor.predict(prompt=current_prompt, draft_output=stage_output[0],
+                                                  draft_logprobs=stage_logprobs[0] if len(stage_logprobs) else None,
+                                                  stage_id=stage_idx, feature_extractor=self.feature_extractor)
+                    if self.config.risk_adjustment:
+                        n_obs = max(100, self.stats["total_requests"])                       # :235
+                        prob = bayesian_adjustment(prob, n_obs, self.config.risk_alpha, self.config.risk_beta)
+                    probabilities.append(prob)
+                else:
+                    probabilities.append(1.0)                                                # :241-242
+                stop, k_star = self._decide(probabilities, costs, stage_idx, len(stage_names), all_costs)
             if stop:
                 break
             if stage_idx < len(stage_names) - 1:
@@ -247,11 +274,25 @@ class AdaptiveSpeculativePipeline:
                 texts, logprobs, _ = stage.generate(prompts=[st[i]["cur"] for i in live], max_tokens=max_tokens,
                                                     temperature=temperature, return_logprobs=True)
                 nxt = []
+                dev = self._device_decide(stage, [st[i]["cur"] for i in live], texts,
+                                          [logprobs[j] if len(logprobs) > j else None for j in range(len(live))],
+                                          [st[i]["probs"] for i in live],
+                                          st[live[0]]["costs"] + [stage.cost_per_token], all_costs, stage_idx,
+                                          len(names), n_obs)
                 for j, i in enumerate(live):
                     r = st[i]
                     r["outs"].append(texts[j])
                     r["costs"].append(stage.cost_per_token)
                     r["tokens"] += len(texts[j].split())
+                    if dev is not None:
+                        r["probs"].append(float(dev[0][j]))
+                        stop, k_star = bool(dev[1][j]), int(dev[2][j])
+                        if stop or stage_idx == len(names) - 1:
+                            r["k"] = k_star
+                        else:
+                            r["cur"] = r["prompt"] + " " + texts[j]
+                            nxt.append(i)
+                        continue
                     if stage_idx < len(names) - 1:
                         lp = logprobs[j] if len(logprobs) > j else None
                         prob = self.predictor.predict(prompt=r["cur"], draft_output=texts[j], draft_logprobs=lp,

@@ -56,7 +56,8 @@ ASD_API void asd_reset_launch_count(void);
  * token per row from softmax(target/T) (used for the draft model's own sampling).
  */
 ASD_API size_t asd_reject_sample_workspace_bytes(int B, int k);
-/* deprecated no-op (round 1 had two kernels behind one arithmetic contract; there is one streaming implementation now) */
+/* tuning switch of the streaming sampler (bit flags, default 5: 4 = the draw kernel is gated per sequence, 2 = persistent
+ * statistics CTAs, 8 = single acq_rel ticket); every setting implements the same arithmetic contract bit for bit */
 ASD_API void asd_reject_sample_set_impl(int impl);
 ASD_API int asd_reject_sample(const float* target_logits, const float* draft_logits, const int32_t* draft_tokens,
                       const double* u_accept, const double* u_resid, int B, int k, int V, float temperature,
@@ -81,6 +82,23 @@ ASD_API int asd_stop_rule_rows(const double* p, const double* C, const double* l
                        double alpha, double beta, int32_t* k_star, double* J, void* stream);
 ASD_API int asd_stop_rule_rows_host(const double* p, const double* C, const double* lam, int n, int L, int risk_adjustment,
                             double alpha, double beta, int32_t* k_star, double* J);
+/* Scorer -> stop decision in ONE launch, all on the device (north star 3; replaces the chain
+ * FeatureExtractor.extract -> QualityPredictor.predict -> bayesian_adjustment -> optimal_stopping_rule of
+ * src/serving/pipeline.py:225-256 for n requests that have just finished stage `stage_idx`):
+ *   features fp32 [n, T, ASD_NUM_FEATURES]: the rows asd_reject_sample wrote for each request's generated tokens (still
+ *     in device memory); n_tokens i32 [n]: how many of the T rows are valid;
+ *   scalars fp64 [n, 3]: prompt words / 2048, output words / 512, stage / 4 (RESEARCH_PROTOCOL.md:389-403);
+ *   w1 fp32 [128, feature_dim], b1 [128], w2 [128], b2 [1]: the 256 -> 128 -> 1 MLP (RESEARCH_PROTOCOL.md:325-331);
+ *   prev_p fp64 [n, L]: acceptance probabilities of the stages before stage_idx; C fp64 [L]: stage costs;
+ *   prefix_mode 1: the reference loop's rule (DP over the stages seen so far, stop iff k* == stage_idx, pipeline.py:248-256),
+ *   0: DP over all L stages with unseen stages at probability 1 (stop iff k* <= stage_idx).
+ * Outputs: prob fp64 [n] (after the optional Bayesian shrinkage with n_obs; 1.0 at the last stage), stop i32 [n],
+ * k_star i32 [n].  The host reads three numbers per request; no per-token data leaves the device. */
+ASD_API int asd_cascade_decide(const float* features, const int32_t* n_tokens, int n, int T, const double* scalars,
+                       const float* w1, const float* b1, const float* w2, const float* b2, int feature_dim,
+                       const double* prev_p, const double* C, int L, int stage_idx, int prefix_mode, double lam,
+                       int risk_adjustment, double n_obs, double alpha, double beta, double* prob, int32_t* stop,
+                       int32_t* k_star, void* stream);
 /* scalar host form used by the Python policy seam (pipeline.py:251-256): returns k_star or -1 */
 ASD_API int asd_stop_rule_host(const double* p, const double* C, int L, double lam, int risk_adjustment, double alpha,
                        double beta, double* J);

@@ -22,15 +22,17 @@
  *   belongs to lane ((u / 4) mod 256) and a lane visits its (up to 16) elements in increasing u.
  *     a_v  = z_v * c1;   m_c = max a_v over the chunk;  (m_c, m2_c) = two largest of the multiset
  *     t_v  = fmaf(z_v, c1, -m_c);     e_v = exp2p(t_v)      (degree-5 polynomial below)
- *     lane sums of e_v and of e_v * t_v (left to right from 0), then wsum: Hillis-Steele inclusive scan
- *     inside each group of 32 lanes, a sequential chain over the 8 groups (its last value is the total).
+ *     lane sums of e_v and of e_v * t_v: a lane keeps two running sums, one over its elements with even local
+ *     index and one over the odd ones (each left to right from 0), and adds them (even + odd) at the end;
+ *     then wsum: Hillis-Steele inclusive scan inside each group of 32 lanes, a sequential chain over the 8
+ *     groups (its last value is the total).
  *   Row merge, sequential over the chunks:  M = max m_c;  s_c = exp2p(m_c - M);
  *     Z = sum_c Z_c * s_c;   S = sum_c fmaf(Z_c, m_c - M, S_c) * s_c;   second maximum by the usual merge.
  *   A probability is never formed; P_v = e_v * s_c is "p_v * Z".
  *   accept:  (u * (double)Q_x) * (double)Zp  <=  (double)P_x * (double)Zq                 (binary64)
  *   Only the row that emits the sequence's new token (the first rejected position, or the bonus row)
  *   draws from the residual  r_v = max(0, fmaf(P_v, Zq, -(Q_v * Zp)))  (bonus row: r_v = P_v):
- *     chunk totals R_c by lane sums + wsum, R = sequential sum, tau = ur * R (0 if that is not < R);
+ *     chunk totals R_c by lane sums (ONE running sum per lane here, left to right) + wsum, R = sequential sum, tau = ur * R (0 if that is not < R);
  *     the first chunk whose running total exceeds tau, inside it the first lane whose inclusive scan value
  *     X + (off_group + hs_lane) exceeds tau (X = running total before the chunk), inside the lane the
  *     first element whose running sum (started from the previous lane's scan value) exceeds tau.
@@ -114,7 +116,7 @@ static void row_stats(const float *z, int V, float c1, float *e, row_t *R)
     R->nc = (V + CHUNK - 1) / CHUNK;
     for (c = 0; c < R->nc; ++c) {
         const int v0 = c * CHUNK, n = (V - v0) < CHUNK ? (V - v0) : CHUNK;
-        float laneZ[LANES], laneS[LANES];
+        float laneZ[2][LANES], laneS[2][LANES], lz[LANES], ls[LANES];
         float m1 = -INFINITY, m2 = -INFINITY;
         for (i = 0; i < n; ++i) {
             float a = z[v0 + i] * c1;
@@ -132,13 +134,17 @@ static void row_stats(const float *z, int V, float c1, float *e, row_t *R)
             const float t = fmaf(z[v0 + i], c1, -m1);
             const float ex = exp2p(t);
             e[v0 + i] = ex;
-            laneZ[l] = laneZ[l] + ex;
-            laneS[l] = laneS[l] + ex * t;
+            laneZ[i & 1][l] = laneZ[i & 1][l] + ex;
+            laneS[i & 1][l] = laneS[i & 1][l] + ex * t;
+        }
+        for (i = 0; i < LANES; ++i) {
+            lz[i] = laneZ[0][i] + laneZ[1][i];
+            ls[i] = laneS[0][i] + laneS[1][i];
         }
         R->m[c] = m1;
         R->m2[c] = m2;
-        R->Z[c] = wsum(laneZ);
-        R->S[c] = wsum(laneS);
+        R->Z[c] = wsum(lz);
+        R->S[c] = wsum(ls);
     }
     R->M = -INFINITY;
     R->M2 = -INFINITY;
