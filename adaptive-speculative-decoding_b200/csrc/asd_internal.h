@@ -43,6 +43,7 @@ struct Tuning {
     int gemm_next_mb = 0;   // L2 budget (MB) for the next kernel's weights; measured neutral, off
     int glue_pdl = 1;       // launch the glue kernels programmatically (they wait on griddepcontrol)
     int attn_wide = 0;
+    int attn_dbg = 0;       // diagnostics (tcgen05 attention): 1 = skip the softmax arithmetic, 2 = also skip the fold
     int gemm_big = 1;       // token counts above the HBM/tensor ridge use the 2-CTA tensor-bound GEMM
 };
 extern thread_local const Tuning* g_tuning;

@@ -85,6 +85,8 @@ struct AttnArgs {
     int* tickets;                  // [nseq_max * nkv], zero between launches
     __nv_bfloat16* out;            // [M, nh, hd]
     unsigned long long* trace;     // diagnostics: 16 globaltimer stamps per CTA (nullptr = off)
+    // weights of the following GEMMs to pull into L2 while this kernel runs (see AttnLaunch::WeightPrefetch)
+    int pf_ntiles[2], pf_ksplit[2], pf_kblocks[2], pf_kp[2];
 };
 
 __device__ __forceinline__ void attn_stamp(const AttnArgs& a, int slot) {
@@ -96,11 +98,33 @@ __device__ __forceinline__ void attn_stamp(const AttnArgs& a, int slot) {
     }
 }
 
+// L2 prefetch of the weights the next GEMMs will stream: 16 KB boxes, k-block-major (the first k-block of every
+// CTA of that GEMM first, so all of its CTAs find the same share of their slab in L2), dealt round-robin over
+// this grid's CTAs and `nissue` threads per CTA
+__device__ __forceinline__ void attn_prefetch_weights(const AttnArgs& a, int i, const CUtensorMap* tmap, int who,
+                                                      int nissue) {
+    const int ntiles = a.pf_ntiles[i], ksplit = a.pf_ksplit[i], kblocks = a.pf_kblocks[i], kp = a.pf_kp[i];
+    if (kp <= 0) return;
+    const int ncta_next = ntiles * ksplit, nbox = ncta_next * kp;
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int nthr = gridDim.x * gridDim.y * gridDim.z * nissue;
+    const int nbase = kblocks / ksplit, nrem = kblocks % ksplit;
+    for (int b = cta * nissue + who; b < nbox; b += nthr) {
+        const int j = b / ncta_next, c = b - j * ncta_next;
+        const int nt = c % ntiles, ns = c / ntiles;
+        const int nkb_c = nbase + (ns < nrem ? 1 : 0);
+        if (j >= nkb_c) continue;
+        const int kb = ns * nbase + (ns < nrem ? ns : nrem) + j;
+        tma_prefetch_l2_2d(tmap, kb * 64, nt * 128);
+    }
+}
+
 // HD = head_dim (64 or 128); KW = keys of each 64-key tile handled by one warp (64, 32 or 16).
 // warp w = (row group w % rg_count, key group w / rg_count): 16 query rows x KW keys per tile.
 // NS = depth of the cp.async K/V ring (4 when there is one CTA per SM, 2 otherwise).
 template <int HD, int KW, int NS>
-__global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a, const __grid_constant__ CUtensorMap tmap_pf0,
+                                                       const __grid_constant__ CUtensorMap tmap_pf1) {
     constexpr int CH = HD / 8;          // 16-byte chunks per row
     constexpr int ROWB = HD * 2;        // bytes per row
     constexpr int KB = HD / 16;         // k-blocks over head_dim
@@ -172,6 +196,10 @@ __global__ void __launch_bounds__(256) attn_mma_kernel(const AttnArgs a) {
     attn_stamp(a, 2);
     grid_dep_wait();   // q and the new K/V come from the QKV GEMM launched just before
     grid_dep_launch();
+    if (threadIdx.x < 4) {   // HBM is otherwise idle from here on: pull the next GEMMs' weights into L2
+        attn_prefetch_weights(a, 0, &tmap_pf0, threadIdx.x, 4);
+        attn_prefetch_weights(a, 1, &tmap_pf1, threadIdx.x, 4);
+    }
 
     // ---- stage Q (rows r = t*G + gq -> token q0+t, head g*G+gq), swizzled
     for (int c = threadIdx.x; c < a.rg_count * 16 * CH; c += blockDim.x) {
@@ -453,7 +481,8 @@ unsigned long long* g_attn_trace = nullptr;
 int g_attn_trace_max = 0, g_attn_trace_next = 0;
 
 template <int HD, int KW, int NS>
-static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t stream) {
+static int launch_mma(const AttnArgs& a, const CUtensorMap& pf0, const CUtensorMap& pf1, dim3 grid, int threads,
+                      size_t smem, cudaStream_t stream) {
     static PerDeviceOnce once;
     if (once.need()) {
         ASD_CUDA(cudaFuncSetAttribute(attn_mma_kernel<HD, KW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -470,7 +499,7 @@ static int launch_mma(const AttnArgs& a, dim3 grid, int threads, size_t smem, cu
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = tuning().glue_pdl ? 1 : 0;
-    ASD_CUDA(cudaLaunchKernelEx(&cfg, attn_mma_kernel<HD, KW, NS>, a));
+    ASD_CUDA(cudaLaunchKernelEx(&cfg, attn_mma_kernel<HD, KW, NS>, a, pf0, pf1));
     return 0;
 }
 
@@ -488,7 +517,7 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     }
     const int G = L.nh / L.nkv;
     const int rows = L.max_qlen * G;
-    if (L.impl == 2 && L.kv_map != nullptr && L.hd == 128 && L.page_size == 16 && rows <= 128)
+    if (L.impl == 2 && L.kv_map != nullptr && L.hd == 128 && rows <= 128 && L.split_keys % 128 == 0)
         return launch_attention_tc(L, stream);
     const int rg = (rows + 15) / 16;
     if (rg > 8) return set_error("attention: q_len * group = %d rows exceeds 128; chunk the query", rows);
@@ -532,8 +561,18 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     if (kg > 1 && merge > smem) smem = merge;
     const int kw = kKeyTile / kg, th = warps * 32;
     int rc;
-#define ASD_ATTN(HD_, KW_) (ns == 4 ? launch_mma<HD_, KW_, 4>(a, grid, th, smem, stream) \
-                                    : launch_mma<HD_, KW_, 2>(a, grid, th, smem, stream))
+    static const CUtensorMap no_map = {};
+    const CUtensorMap* pfm[2] = {&no_map, &no_map};
+    for (int i = 0; i < 2; ++i) {
+        const bool on = L.pf[i].tmap != nullptr && L.pf[i].kp > 0;
+        a.pf_ntiles[i] = L.pf[i].ntiles;
+        a.pf_ksplit[i] = L.pf[i].ksplit > 0 ? L.pf[i].ksplit : 1;
+        a.pf_kblocks[i] = L.pf[i].kblocks;
+        a.pf_kp[i] = on ? L.pf[i].kp : 0;
+        if (on) pfm[i] = L.pf[i].tmap;
+    }
+#define ASD_ATTN(HD_, KW_) (ns == 4 ? launch_mma<HD_, KW_, 4>(a, *pfm[0], *pfm[1], grid, th, smem, stream) \
+                                    : launch_mma<HD_, KW_, 2>(a, *pfm[0], *pfm[1], grid, th, smem, stream))
     if (L.hd == 128)
         rc = kw == 64 ? ASD_ATTN(128, 64) : (kw == 32 ? ASD_ATTN(128, 32) : ASD_ATTN(128, 16));
     else

@@ -66,10 +66,10 @@ struct Engine {
     std::unordered_map<int, std::pair<GemmPlan, CUtensorMap>> lm_plans;  // keyed by rows (xnorm) / -rows (xsel)
     std::unordered_map<int, std::pair<TcPlan, CUtensorMap>> lm_plans_tc;
     // options
-    // attn_impl: 1 = mma.sync kernel (default: measured faster on every bench shape, tools/bench_attn.py), 2 = tcgen05
-    // kernel (attention_tc.cu; correct, but its single softmax warpgroup keeps it behind: 47 vs 22 us at 32B/prefix 512,
-    // 234 vs 179 us at 72B-TP4/prefix 4096), 0 = one-warp cross-check kernel
-    int attn_impl = 1, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
+    // attn_impl: 2 = tcgen05 kernel (attention_tc.cu; default: faster on every bench shape since P moved into TMEM -
+    // 18.7 vs 22.8 us at 32B/prefix 512, 64 vs 180 us at 72B-TP4/prefix 4096, tools/bench_attn.py), 1 = mma.sync kernel
+    // (also the fallback for head_dim 64 or more than 128 query rows), 0 = one-warp cross-check kernel
+    int attn_impl = 2, pdl = 1, force_ksplit = 0, force_stages = 0, max_attn_splits = 16, reduce = 1,
         attn_target_ctas = 148, fuse_rope = 1, fuse_norm = 0, attn_min_split_keys = 1024, tp_fused = 1, tp_two_shot = 0;
     Tuning tune;   // per-engine knobs, installed for the calling thread by forward()
     // persistent forward kernel (forward_persist.cu): one cooperative launch per forward when the shape allows
@@ -77,6 +77,8 @@ struct Engine {
     // phase boundary through global memory (partials -> flags -> reduce -> epilogue -> counter -> X load) costs 15-18 us
     // against 10-12 us for a kernel boundary under programmatic dependent launch, so it is opt-in (option persist = 1)
     int persist = 0, persist_ahead = 0;
+    // MB of the O-projection / gate|up weights that the attention kernel pulls into L2 while it runs (0 = off)
+    int attn_prefetch_mb = 0;
     PLayer* p_layers = nullptr;      // device array, rebuilt lazily after set_layer / set_kv
     bool p_layers_ok = false;
     unsigned* p_sync = nullptr;
@@ -190,8 +192,8 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
     if (nsplit > max_by_len) nsplit = max_by_len;
     if (nsplit > e->max_attn_splits) nsplit = e->max_attn_splits;
     if (nsplit < 1) nsplit = 1;
-    int split_keys = ((max_kv_len + nsplit - 1) / nsplit + 63) / 64 * 64;
-    if (split_keys < 64) split_keys = 64;
+    int split_keys = ((max_kv_len + nsplit - 1) / nsplit + 127) / 128 * 128;   // whole key tiles of both kernels
+    if (split_keys < 128) split_keys = 128;
     const int nsplit_max = (max_kv_len + split_keys - 1) / split_keys;
     if ((size_t)M * nh * nsplit_max * hd > e->o_part_floats) return set_error("engine: attention workspace too small");
 
@@ -438,6 +440,26 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         A.kv_map = e->kv_map_ok ? &e->kv_map : nullptr;
         A.k_row0 = (long long)(2 * l) * e->num_pages * nkv * c.page_size;
         A.v_row0 = A.k_row0 + (long long)e->num_pages * nkv * c.page_size;
+        if (e->attn_prefetch_mb > 0) {
+            // all of W_o first, what is left of the budget as the first k-blocks of every gate|up CTA
+            long long budget = (long long)e->attn_prefetch_mb << 20;
+            const GemmPlan* gp[2] = {&P->o, P->use_tc ? nullptr : &P->gu};
+            const CUtensorMap* gm[2] = {&L.t_o, &L.t_gu};
+            for (int i = 0; i < 2; ++i) {
+                if (gp[i] == nullptr || gp[i]->m_tiles != 1 || budget <= 0) continue;
+                const long long ncta = (long long)gp[i]->n_tiles * gp[i]->ksplit;
+                const int per_cta = (gp[i]->kblocks + gp[i]->ksplit - 1) / gp[i]->ksplit;
+                int kp = (int)(budget / (ncta * 16384));
+                if (kp > per_cta) kp = per_cta;
+                if (kp <= 0) continue;
+                A.pf[i].tmap = gm[i];
+                A.pf[i].ntiles = gp[i]->n_tiles;
+                A.pf[i].ksplit = gp[i]->ksplit;
+                A.pf[i].kblocks = gp[i]->kblocks;
+                A.pf[i].kp = kp;
+                budget -= (long long)kp * ncta * 16384;
+            }
+        }
         {
             PROF(PROF_ATTN);
             if (launch_attention(A, s)) return -1;
@@ -644,8 +666,9 @@ int asd_engine_set_kv(asd_engine_t* h, void* kv_pool, int num_pages, const int32
     e->kv_map_ok = false;
     e->p_layers_ok = false;
     const unsigned long long rows = 2ull * e->c.n_layers * num_pages * e->c.n_kv_heads * e->c.page_size;
-    if (e->c.head_dim == 128 && e->c.page_size == 16 && rows < (1ull << 31)) {
-        if (make_tmap_bf16(&e->kv_map, kv_pool, rows, 128, 128, 16)) return -1;
+    const int ps = e->c.page_size;
+    if (e->c.head_dim == 128 && (ps == 16 || ps == 32 || ps == 64 || ps == 128) && rows < (1ull << 31)) {
+        if (make_tmap_bf16(&e->kv_map, kv_pool, rows, 128, 128, ps)) return -1;   // box = one page x 64 elements
         e->kv_map_ok = true;
     }
     return 0;
@@ -771,6 +794,8 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "fuse_rope")) e->fuse_rope = value;
     else if (!strcmp(name, "glue_pdl")) e->tune.glue_pdl = value;
     else if (!strcmp(name, "attn_wide")) e->tune.attn_wide = value;
+    else if (!strcmp(name, "attn_dbg")) e->tune.attn_dbg = value;
+    else if (!strcmp(name, "attn_prefetch_mb")) e->attn_prefetch_mb = value;
     else if (!strcmp(name, "gemm_big")) e->tune.gemm_big = value;
     else if (!strcmp(name, "persist")) e->persist = value;
     else if (!strcmp(name, "persist_ahead")) e->persist_ahead = value;

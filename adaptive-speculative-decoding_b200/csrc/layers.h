@@ -46,6 +46,13 @@ struct AttnLaunch {
     // elements (box = 64 elements x 16 positions) and the first row of this layer's K / V
     const CUtensorMap* kv_map = nullptr;
     long long k_row0 = 0, v_row0 = 0;
+    // L2 prefetch of the weights of the GEMMs that follow (O projection, then gate|up), issued by this kernel's CTAs
+    // once the QKV GEMM upstream has finished: attention streams ~1.5 TB/s of K/V, the rest of the HBM bandwidth
+    // is idle for its whole duration (engine option attn_prefetch_mb; mma.sync kernel only)
+    struct WeightPrefetch {
+        const CUtensorMap* tmap = nullptr;   // weight map of the GEMM (box = 64 k x 128 rows)
+        int ntiles = 0, ksplit = 1, kblocks = 0, kp = 0;   // kp = k-blocks per CTA of that GEMM to prefetch
+    } pf[2];
 };
 // impl 0: one-warp cross-check kernel; 1: mma.sync kernel; 2: tcgen05 kernel when the shape allows (head_dim 128,
 // 16-position pages, q_len * group <= 128), else 1

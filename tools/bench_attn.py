@@ -14,12 +14,15 @@ from asd_b200.models.qwen2 import QWEN25
 PEAK = 6548.8
 
 
+PAGE = int(os.environ.get("ASD_PAGE", "16"))
+
+
 def run(name, cfg, B, q, prefix, tp, impls=(1, 2), opts=()):
     cfg2 = replace(cfg, num_hidden_layers=2)
     M = B * q
     for impl in impls:
-        eng = QwenEngine(cfg2, max_seqs=B, max_seq_len=prefix + 64, max_tokens=max(M, 256), tp_rank=0, tp_size=tp,
-                         device="cuda:0")
+        eng = QwenEngine(cfg2, max_seqs=B, max_seq_len=prefix + 64, max_tokens=max(M, 256), page_size=PAGE,
+                         tp_rank=0, tp_size=tp, device="cuda:0")
         eng.load_random(seed=3)
         if tp > 1:   # a lone rank of a tp-way split: boundaries through a no-op "all-reduce" is not available; use p2p off + tp 1 dims
             raise SystemExit("use local dims instead of tp")
@@ -46,7 +49,7 @@ def run(name, cfg, B, q, prefix, tp, impls=(1, 2), opts=()):
         nbytes = B * (prefix + q) * 2 * nkv * hd * 2
         print(json.dumps(dict(shape=name, impl=impl, B=B, q=q, prefix=prefix, nh=cfg2.num_attention_heads, nkv=nkv,
                               us=round(us, 2), GBs=round(nbytes / us / 1e3, 1), frac=round(nbytes / us / 1e3 / PEAK, 3),
-                              opts=list(opts))), flush=True)
+                              opts=list(opts), page=PAGE)), flush=True)
         eng.close()
         del eng
         torch.cuda.empty_cache()
