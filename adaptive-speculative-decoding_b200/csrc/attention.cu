@@ -583,6 +583,25 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     return 0;
 }
 
+// see preload_layers()
+int preload_attention() {
+    cudaFuncAttributes fa;
+    ASD_CUDA(cudaFuncGetAttributes(&fa, attn_simple_kernel));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<64, 64, 2>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<64, 64, 4>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<64, 32, 2>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<64, 32, 4>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<64, 16, 2>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<64, 16, 4>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<128, 64, 2>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<128, 64, 4>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<128, 32, 2>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<128, 32, 4>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<128, 16, 2>)));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, (attn_mma_kernel<128, 16, 4>)));
+    return 0;
+}
+
 }  // namespace asd
 
 extern "C" __attribute__((visibility("default"))) int asd_debug_attn_trace(unsigned long long* buf, int max_launches) {

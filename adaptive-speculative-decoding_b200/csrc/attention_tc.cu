@@ -551,4 +551,12 @@ int launch_attention_tc(const AttnLaunch& L, cudaStream_t stream) {
     return 0;
 }
 
+// Force the (lazily loaded) kernels of this file into the context now: a first launch that loads a kernel may need a
+// context synchronisation, which deadlocks when another rank of the same process is spinning for this rank's launch.
+int preload_attention_tc() {
+    cudaFuncAttributes fa;
+    ASD_CUDA(cudaFuncGetAttributes(&fa, attn_tc_kernel));
+    return 0;
+}
+
 }  // namespace asd

@@ -545,6 +545,12 @@ asd_engine_t* asd_engine_create(const asd_model_config* cfg) {
         set_error("asd_engine_create: unsupported model shape");
         return nullptr;
     }
+    {   // lazy module loading + spinning tensor-parallel kernels in one process = deadlock: load everything now
+        static PerDeviceOnce loaded;
+        if (loaded.need() && (preload_layers() || preload_attention() || preload_attention_tc() || preload_gemm() ||
+                              preload_gemm_tc()))
+            return nullptr;
+    }
     Engine* e = new Engine();
     e->c = c;
     cudaGetDevice(&e->device);

@@ -867,6 +867,14 @@ int gemm_launch(const GemmPlan& pl, const CUtensorMap& tmap_w, const CUtensorMap
     return 0;
 }
 
+// Force the (lazily loaded) kernels of this file into the context now: a first launch that loads a kernel may need a
+// context synchronisation, which deadlocks when another rank of the same process is spinning for this rank's launch.
+int preload_gemm() {
+    cudaFuncAttributes fa;
+    ASD_CUDA(cudaFuncGetAttributes(&fa, gemm_ws_kernel));
+    return 0;
+}
+
 }  // namespace asd
 
 // ------------------------------------------------------------------------------------------- C ABI

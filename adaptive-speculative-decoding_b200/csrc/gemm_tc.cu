@@ -426,6 +426,14 @@ int gemm_tc_launch(const TcPlan& pl, const CUtensorMap& tmap_w, const CUtensorMa
     return 0;
 }
 
+// Force the (lazily loaded) kernels of this file into the context now: a first launch that loads a kernel may need a
+// context synchronisation, which deadlocks when another rank of the same process is spinning for this rank's launch.
+int preload_gemm_tc() {
+    cudaFuncAttributes fa;
+    ASD_CUDA(cudaFuncGetAttributes(&fa, gemm_tc_kernel));
+    return 0;
+}
+
 }  // namespace asd
 
 #include "../../include/asd_b200.h"

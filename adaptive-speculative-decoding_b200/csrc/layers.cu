@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "asd_internal.h"
 #include "layers.h"
 #include "ptx.cuh"
@@ -446,6 +448,19 @@ static void glue_carveout() {
     prefer_max_smem(qkv_rope_kernel);
     prefer_max_smem(rope_table_kernel);
     prefer_max_smem(gather_rows_kernel);
+}
+
+// Force the (lazily loaded) kernels of this file into the context now: a first launch that loads a kernel may need a
+// context synchronisation, which deadlocks when another rank of the same process is spinning for this rank's launch.
+int preload_layers() {
+    cudaFuncAttributes fa;
+    ASD_CUDA(cudaFuncGetAttributes(&fa, add_norm_kernel));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, tp_allreduce_norm_kernel));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, reduce_slices_kernel));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, qkv_rope_kernel));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, rope_table_kernel));
+    ASD_CUDA(cudaFuncGetAttributes(&fa, gather_rows_kernel));
+    return 0;
 }
 
 }  // namespace asd

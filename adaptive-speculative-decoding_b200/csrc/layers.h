@@ -59,4 +59,11 @@ struct AttnLaunch {
 int launch_attention(const AttnLaunch& L, cudaStream_t stream);
 int launch_attention_tc(const AttnLaunch& L, cudaStream_t stream);
 
+// load every kernel of the forward into the current context (see layers.cu: preload_layers)
+int preload_layers();
+int preload_attention();
+int preload_attention_tc();
+int preload_gemm();
+int preload_gemm_tc();
+
 }  // namespace asd

@@ -219,7 +219,15 @@ def config5(torch, dist, rank, world, dev, args, peaks):
     M = B * (k + 1)
     eng = QwenEngine(cfg, max_seqs=B, max_seq_len=prefix + 64, max_tokens=M, tp_rank=rank, tp_size=world, device=dev)
     eng.load_random(seed=2)
-    eng.enable_p2p()
+    if args.nccl_only:                # development aid: the exchange through ncclAllReduce instead of the peer kernels
+        from asd_b200.parallel import NcclComm
+        comm5 = NcclComm(rank, world)
+        eng.set_allreduce(comm5.comm_ptr, comm5.allreduce_fn_ptr)
+    else:
+        eng.enable_p2p()
+    for o in args.opt or []:          # development aid: engine options also reach this record
+        name, val = o.split("=")
+        eng.set_option(name, int(val))
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     pool = eng.kv_pool
     step = 1 << 28
@@ -248,6 +256,13 @@ def config5(torch, dist, rank, world, dev, args, peaks):
     prof = eng.profile_read()
     eng.set_option("profile", 0)
     tp_err = eng.tp_error()
+    # per-rank view of the profiled classes: a rank that waits for a slower peer books the wait under "allreduce",
+    # so the MINIMUM over ranks is the cost of the exchange itself and the spread is load imbalance between GPUs
+    mine = torch.tensor([prof["gemm"][0], prof["attention"][0], prof["allreduce"][0]], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    per_rank = {"gemm": [round(float(t[0]), 3) for t in allr], "attention": [round(float(t[1]), 3) for t in allr],
+                "allreduce": [round(float(t[2]), 3) for t in allr]}
     dist.barrier()
     eng.close()
     del eng, pool, logits
@@ -264,6 +279,7 @@ def config5(torch, dist, rank, world, dev, args, peaks):
             "frac_of_tensor_floor": tensor_floor_ms / ms, "tflops_per_gpu": (gemm_flops + attn_flops) / (ms * 1e-3) / 1e12,
             "verified_tokens_per_second": M / (ms * 1e-3), "tp_error": int(tp_err),
             "breakdown_ms_profiled": {c: round(v[0], 3) for c, v in prof.items()},
+            "breakdown_ms_per_rank": per_rank,
             "allreduce_bytes_per_boundary": M * cfg.hidden_size * 4, "boundaries": 2 * cfg.num_hidden_layers}
 
 

@@ -80,6 +80,42 @@ def test_tp_inprocess_32b_width_matches_single_gpu(tp):
     assert _decidable_agree(outs[1], outs[0]) >= 0.999
 
 
+@pytest.mark.skipif(NGPU < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("tp,two_shot", [(2, 0), (2, 1), (4, 0), (4, -1), (8, 0)])
+def test_tp_inprocess_large_verify_matches_single_gpu(tp, two_shot):
+    """M = 320 tokens (> 256: the tensor-bound CTA-pair GEMM, BASELINE configs[4]'s regime; 6.5 MB per boundary): O
+    through the weight-streaming kernel with the fused exchange (two ranks) or the all-reduce kernel, down through the
+    CTA-pair kernel + slice reduction + all-reduce kernel (one-shot / two-shot, tp_two_shot forces either).  All must
+    agree with one GPU."""
+    if NGPU < tp:
+        pytest.skip(f"needs {tp} GPUs")
+    from asd_b200.engine import QwenEngine, TPQwenEngine
+    cfg = replace(QWEN25["32b"], num_hidden_layers=2)
+    w = random_hf_weights(cfg, seed=3, device="cuda:0", logit_std=0.25)
+    B, P, q = 32, 48, 10
+    ids = torch.randint(0, cfg.vocab_size, (B, P + q), generator=torch.Generator().manual_seed(9)).to("cuda:0").to(torch.int32)
+    slots = torch.arange(B, dtype=torch.int32, device="cuda:0")
+    start = torch.full((B,), P, dtype=torch.int32, device="cuda:0")
+    outs = []
+    for make in (lambda: QwenEngine(cfg, max_seqs=B, max_seq_len=P + q + 16, max_tokens=512, device="cuda:0"),
+                 lambda: TPQwenEngine(cfg, list(range(tp)), max_seqs=B, max_seq_len=P + q + 16, max_tokens=512)):
+        eng = make().load_hf_weights(w)
+        if hasattr(eng, "tp_error"):
+            eng.set_option("tp_two_shot", two_shot)
+        eng.prefill(ids[:, :P], slots, want_logits=False)
+        for _ in range(3):      # several forwards: the receive areas alternate with the epoch parity
+            ver = eng.forward_uniform(ids[:, P:].contiguous(), start, slots, P + q)
+        for d in range(NGPU):
+            torch.cuda.synchronize(d)
+        outs.append(ver.view(B, q, -1).cpu())
+        if hasattr(eng, "tp_error"):
+            assert eng.tp_error() == 0
+        eng.close()
+    err = (outs[0] - outs[1]).abs().max().item()
+    assert err <= 2e-2, err
+    assert _decidable_agree(outs[1], outs[0]) >= 0.999
+
+
 def _cascade_placement():
     """the reference's placement on as many GPUs as the box has (every stage on its own GPUs)"""
     if NGPU >= 7:
