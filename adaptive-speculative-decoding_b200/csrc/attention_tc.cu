@@ -343,8 +343,12 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                     return;
                 }
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                // boundary tile: a 64-key half none of this warp's rows can see is skipped (its probabilities are zeros) -
+                // with a short prefix the last tile holds only the step's own few keys
+                const int wlim = MASKED ? __reduce_max_sync(0xffffffffu, lim) : kAtTile;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (MASKED && wlim < h * 64) continue;
                     uint32_t v0[32], v1[32];
                     tmem_ld_32x32(tS + (uint32_t)(h * 64), v0);
                     tmem_ld_32x32(tS + (uint32_t)(h * 64 + 32), v1);
@@ -363,6 +367,13 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v0[32], v1[32], pk[16];
+                    if (MASKED && wlim < h * 64) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                        at_tmem_st16(tS + (uint32_t)(h * 32), pk);
+                        at_tmem_st16(tS + (uint32_t)(h * 32 + 16), pk);
+                        continue;
+                    }
                     tmem_ld_32x32(tS + (uint32_t)(h * 64), v0);
                     tmem_ld_32x32(tS + (uint32_t)(h * 64 + 32), v1);
                     tmem_ld_wait();

@@ -37,8 +37,8 @@ struct Plans {
     CUtensorMap x_norm, x_attn, x_act;
     // token counts above the HBM/tensor ridge: gate|up and down run on the tensor-bound CTA-pair kernel (gemm_tc.cu)
     bool use_tc = false;
-    TcPlan gu_tc, down_tc;
-    CUtensorMap x_norm_tc, x_act_tc;
+    TcPlan gu_tc, down_tc, qkv_tc, o_tc;
+    CUtensorMap x_norm_tc, x_act_tc, x_norm_qkv_tc, x_attn_tc;
 };
 
 struct Engine {
@@ -79,6 +79,8 @@ struct Engine {
     int persist = 0, persist_ahead = 0;
     // MB of the O-projection / gate|up weights that the attention kernel pulls into L2 while it runs (0 = off)
     int attn_prefetch_mb = 0;
+    // token counts above 256: QKV and O also run on the CTA-pair kernel (0 = weight-streaming kernel as for small steps)
+    int tc_qkvo = 1;
     PLayer* p_layers = nullptr;      // device array, rebuilt lazily after set_layer / set_kv
     bool p_layers_ok = false;
     unsigned* p_sync = nullptr;
@@ -153,6 +155,14 @@ static int ensure_plans(Engine* e, int M, Plans** out) {
         if ((size_t)p.down_tc.ksplit * M * h > e->part_floats) return set_error("engine: split-K workspace too small");
         if (make_tmap_bf16(&p.x_norm_tc, e->fuse_norm ? e->resid_bf : e->xnorm, M, h, h, p.gu_tc.MT / 2)) return -1;
         if (make_tmap_bf16(&p.x_act_tc, e->act, M, e->c.ffn, e->c.ffn, p.down_tc.MT / 2)) return -1;
+        // QKV and O as well: at 576 tokens the weight-streaming kernel spends 59 / 120 us per layer on them (72B, TP4
+        // shard; its per-thread epilogue loops are serial over the tokens), the CTA-pair kernel runs them at ~900 TFLOP/s
+        if (gemm_tc_plan(&p.qkv_tc, M, e->nqkv, h, GEMM_OUT_F32, 0, e->force_stages)) return -1;
+        if (gemm_tc_plan(&p.o_tc, M, h, e->qdim, GEMM_OUT_F32, 0, e->force_stages)) return -1;
+        if ((size_t)p.qkv_tc.ksplit * M * e->nqkv > e->part_floats || (size_t)p.o_tc.ksplit * M * h > e->part_floats)
+            return set_error("engine: split-K workspace too small");
+        if (make_tmap_bf16(&p.x_norm_qkv_tc, e->fuse_norm ? e->resid_bf : e->xnorm, M, h, h, p.qkv_tc.MT / 2)) return -1;
+        if (make_tmap_bf16(&p.x_attn_tc, e->attn, M, e->qdim, e->qdim, p.o_tc.MT / 2)) return -1;
     }
     auto r = e->plans.emplace(M, p);
     *out = &r.first->second;
@@ -382,7 +392,18 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
         Layer& L = e->layers[l];
         __nv_bfloat16* kc = e->kv_pool + (size_t)(2 * l) * e->kv_half;
         __nv_bfloat16* vc = kc + e->kv_half;
-        if (P->qkv.mode == GEMM_OUT_QKV) {   // bias + RoPE + q store + paged K/V append fused into the epilogue
+        if (P->use_tc && e->tune.gemm_big >= 1 && e->tc_qkvo) {   // tensor-bound step: CTA-pair GEMM + one glue kernel
+            {
+                PROF(PROF_GEMM);
+                if (gemm_tc_launch(P->qkv_tc, L.t_qkv, P->x_norm_qkv_tc, e->part, e->nqkv, e->nqkv, (size_t)M * e->nqkv,
+                                   e->pdl, s, false, consumer(e->sumsq)))
+                    return -1;
+            }
+            PROF(PROF_GLUE);
+            if (launch_qkv_rope(e->part, P->qkv_tc.ksplit, (size_t)M * e->nqkv, L.bqkv, positions, token_slot,
+                                e->page_table, e->max_pages, e->inv_freq, e->q, kc, vc, M, nh, nkv, hd, c.page_size, s))
+                return -1;
+        } else if (P->qkv.mode == GEMM_OUT_QKV) {   // bias + RoPE + q store + paged K/V append fused into the epilogue
             PROF(PROF_GEMM);
             QkvEpilogue q;
             q.cs = e->rope_cs;
@@ -465,7 +486,9 @@ static int forward(Engine* e, const int* tokens, const int* positions, const int
             if (launch_attention(A, s)) return -1;
         }
         gemm_set_next(P->gu, &L.t_gu);
-        if (project_residual(P->o, L.t_o, P->x_attn, L.ln2)) return -1;
+        if (P->use_tc && e->tc_qkvo ? project_residual_tc(P->o_tc, L.t_o, P->x_attn_tc, L.ln2)
+                                    : project_residual(P->o, L.t_o, P->x_attn, L.ln2))
+            return -1;
         if (P->use_tc) {
             PROF(PROF_GEMM);
             if (gemm_tc_launch(P->gu_tc, L.t_gu, P->x_norm_tc, e->act, c.ffn, c.ffn, 0, e->pdl, s, false, consumer(e->sumsq)))
@@ -801,6 +824,7 @@ int asd_engine_set_option(asd_engine_t* h, const char* name, int value) {
     else if (!strcmp(name, "glue_pdl")) e->tune.glue_pdl = value;
     else if (!strcmp(name, "attn_wide")) e->tune.attn_wide = value;
     else if (!strcmp(name, "attn_dbg")) e->tune.attn_dbg = value;
+    else if (!strcmp(name, "tc_qkvo")) e->tc_qkvo = value;
     else if (!strcmp(name, "attn_prefetch_mb")) e->attn_prefetch_mb = value;
     else if (!strcmp(name, "gemm_big")) e->tune.gemm_big = value;
     else if (!strcmp(name, "persist")) e->persist = value;

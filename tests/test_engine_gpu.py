@@ -86,6 +86,49 @@ def test_engine_unfused_paths(opts):
     eng.close()
 
 
+@pytest.mark.parametrize("fuse_norm,tc_qkvo", [(True, 1), (True, 0), (False, 1)])
+def test_engine_large_step_vs_oracle(fuse_norm, tc_qkvo):
+    """a 320-token verify step (> 256 tokens: the tensor-bound CTA-pair GEMM for gate|up, down, lm_head and - option
+    tc_qkvo, default - QKV + the RoPE / K-V append glue kernel and O) and a 384-token prefill chunk, against the oracle"""
+    from asd_b200.engine import QwenEngine
+    cfg = Qwen2Config(512, 2, 8, 2, 1024, 4096, head_dim=128, name="g4-large")
+    w = random_hf_weights(cfg, seed=13, logit_std=0.4)
+    B, T, q = 32, 22, 10
+    ids = torch.randint(0, cfg.vocab_size, (B, T), generator=torch.Generator().manual_seed(6))
+    ref = qwen2_forward(w, cfg, ids)
+    eng = QwenEngine(cfg, max_seqs=B, max_seq_len=T + 16, max_tokens=512, fuse_norm=fuse_norm).load_hf_weights(w)
+    eng.set_option("tc_qkvo", tc_qkvo)
+    slots = torch.arange(B, dtype=torch.int32, device="cuda")
+    idc = ids.cuda().to(torch.int32)
+    last = eng.prefill(idc[:, :T - q], slots)          # 32 x 12 = 384 tokens in one chunk
+    start = torch.full((B,), T - q, dtype=torch.int32, device="cuda")
+    ver = eng.forward_uniform(idc[:, T - q:].contiguous(), start, slots, T)
+    torch.cuda.synchronize()
+    check(ver.view(B, q, -1).cpu(), ref[:, T - q:])
+    check(last.cpu(), ref[:, T - q - 1])
+    eng.close()
+
+
+@pytest.mark.parametrize("page_size", [32, 64, 128])
+def test_engine_page_sizes(page_size):
+    """the tcgen05 attention kernel gathers K/V by TMA boxes of one page (16 .. 128 positions) x 64 elements"""
+    from asd_b200.engine import QwenEngine
+    cfg = Qwen2Config(512, 2, 10, 2, 1024, 4096, head_dim=128, name="g5")
+    w = random_hf_weights(cfg, seed=11, logit_std=0.4)
+    B, T, q = 3, 300, 6
+    ids = torch.randint(0, cfg.vocab_size, (B, T), generator=torch.Generator().manual_seed(5))
+    ref = qwen2_forward(w, cfg, ids)
+    eng = QwenEngine(cfg, max_seqs=B, max_seq_len=T + 16, max_tokens=64, page_size=page_size).load_hf_weights(w)
+    eng.set_option("attn_impl", 2)
+    slots = torch.arange(B, dtype=torch.int32, device="cuda")
+    idc = ids.cuda().to(torch.int32)
+    eng.prefill(idc[:, :T - q], slots, want_logits=False)
+    ver = eng.forward_uniform(idc[:, T - q:].contiguous(), torch.full((B,), T - q, dtype=torch.int32, device="cuda"), slots, T)
+    torch.cuda.synchronize()
+    check(ver.view(B, q, -1).cpu(), ref[:, T - q:])
+    eng.close()
+
+
 @pytest.mark.parametrize("attn_impl", [1, 2])
 @pytest.mark.parametrize("min_keys,target", [(128, 592), (64, 2000), (256, 148)])
 def test_attention_key_splits(min_keys, target, attn_impl):
