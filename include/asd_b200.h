@@ -185,7 +185,11 @@ ASD_API int asd_engine_tp_error(asd_engine_t* e);
  * ONE process, rank r on its own device.  Enables peer access between the devices and wires every rank's receive
  * buffers and flags into the others (no IPC, no torchrun).  engines[r] must be rank r of a t-way group. */
 ASD_API int asd_engine_peer_connect(asd_engine_t** engines, int n);
-/* options: "attn_impl" (1 tensor-core kernel, 0 one-warp cross-check kernel), "pdl" (0/1),
+/* options: "attn_impl" (2 tcgen05 / TMEM kernel - default; 1 mma.sync kernel, also the fallback for head_dim 64 or more
+ * than 128 query rows; 0 one-warp cross-check kernel), "tc_qkvo" (1, default: above 256 tokens QKV and O run on the
+ * CTA-pair tensor-bound GEMM like gate|up / down / lm_head; 0: weight-streaming kernel), "gemm_big" (0: never use the
+ * CTA-pair GEMM), "attn_prefetch_mb" (L2 prefetch of the following GEMMs' weights from the attention kernel, measured
+ * slower, default 0), "pdl" (0/1),
  * "reduce" (1 in-cluster split-K reduction with fused residual add, 0 fp32 slices summed by the glue
  * kernels), "fuse_rope" (1: bias + RoPE + q store + paged K/V append in the QKV GEMM epilogue),
  * "fuse_norm" (1: RMSNorm fused into the GEMMs: the O / down epilogues emit bf16(resid * ln_w) and the

@@ -1,3 +1,5 @@
+"""Raw NVLink peer bandwidth of the box (torch copies between two GPUs): the yardstick for the tensor-parallel
+exchange numbers in DESIGN.md section 4 (measured: 734 GB/s for cudaMemcpyPeer 1 -> 0 on 2 x B200)."""
 import torch, time
 n = torch.cuda.device_count()
 print("gpus", n)
@@ -25,11 +27,3 @@ for _ in range(10):
             b[i].copy_(a[(i+1)%n], non_blocking=True)
 sync(); dt=time.perf_counter()-t
 print("ring pull per gpu", sz*10/dt/1e9, "GB/s")
-# SM-driven pull: elementwise add with a peer tensor as input (kernel on device 0 reading device 1 memory)
-x1 = a[1].view(torch.float32); y0 = b[0].view(torch.float32)
-torch.cuda.set_device(0)
-for rep in range(2):
-    sync(); t=time.perf_counter()
-    for _ in range(10): torch.add(x1, 1.0, out=y0)   # may fail if torch refuses cross-device
-    sync(); dt=time.perf_counter()-t
-    print("SM pull 1->0 (torch.add)", sz*10/dt/1e9, "GB/s")

@@ -2,7 +2,7 @@
 for ncu launch lists of the per-rank GEMM / attention shapes."""
 import os, sys
 from dataclasses import replace
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from asd_b200.engine import QwenEngine
 from asd_b200.models.qwen2 import QWEN25

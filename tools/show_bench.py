@@ -1,3 +1,4 @@
+"""Print the headline fields of bench.py JSON lines:  python tools/show_bench.py 'gpurun_out/*.json'"""
 import glob, json, sys
 for f in sorted(glob.glob(sys.argv[1])):
     try:
