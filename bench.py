@@ -68,6 +68,50 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
+class Watchdog(threading.Thread):
+    """N > 1 only: the tensor-parallel kernels spin for their peers on the device and a stuck collective cannot be
+    cancelled from the host, so a stage that overruns its budget would otherwise hang the whole job until the caller's
+    own limit.  Every rank runs one; when a stage overruns, rank 0 prints what it has - the finished bench line with a
+    "watchdog" entry if the timed region is done, else an error record - and every rank leaves with os._exit."""
+
+    def __init__(self, rank, world):
+        super().__init__(daemon=True)
+        self.rank, self.world = rank, world
+        self.name_, self.deadline, self.line, self.lock = "start", None, None, threading.Lock()
+
+    def stage(self, name, budget_s):
+        with self.lock:
+            self.name_, self.deadline = name, (time.time() + budget_s if budget_s else None)
+        sys.stderr.write(f"[bench rank {self.rank}] {time.strftime('%H:%M:%S')} stage {name}\n")
+        sys.stderr.flush()
+
+    def run(self):
+        while True:
+            time.sleep(0.5)
+            with self.lock:
+                name, deadline, line = self.name_, self.deadline, self.line
+            if deadline is None or time.time() < deadline:
+                continue
+            msg = f"stage '{name}' did not finish within its budget on rank {self.rank}"
+            sys.stderr.write(f"[bench rank {self.rank}] watchdog: {msg}\n")
+            sys.stderr.flush()
+            code = 5
+            if line is not None:
+                code = 0 if name == "config5" else 3
+                if self.rank == 0:
+                    line = dict(line)
+                    line["watchdog"] = msg
+                    if name == "config5":
+                        line["config5"] = {"error": msg}
+                    else:
+                        line["tp_check"] = {"ok": False, "error": msg}
+                    print(json.dumps(line), flush=True)
+            elif self.rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": self.world,
+                                  "error": "watchdog: " + msg}), flush=True)
+            os._exit(code)
+
+
 def workload(args):
     from asd_b200.models.qwen2 import QWEN25
     target = QWEN25["72b" if args.workload == "72b" else "32b"]
@@ -399,6 +443,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     wl = workload(args)
+    wd = Watchdog(rank, world)
+    if world > 1:
+        wd.start()
+    wd.stage("setup + prefill", 180 if world > 1 else 0)
     if args.config5_only:       # development aid: only the 72B verify-only record
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
@@ -439,6 +487,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    wd.stage("warm-up + timed steps + e2e + profile", 180 if world > 1 else 0)
     for _ in range(args.warmup):
         dec.step()
     barrier()
@@ -503,8 +552,6 @@ def run_ours(args):
         e.set_option("profile", 0)
     ps = max(args.profile_steps, 1)
 
-    tpc = tp_check(torch, dist, rank, world, dev, dec, target, wl["target"]) if world > 1 else None
-
     # max over ranks
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -563,7 +610,13 @@ def run_ours(args):
             "draft_breakdown_ms": {c: round(v[0] / ps / max(k, 1), 4) for c, v in prof_d.items()},
             "step_hbm_frac": step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak,
         }
-        if tpc is not None:
+    tpc = None
+    if world > 1:
+        with wd.lock:
+            wd.line = line if rank == 0 else {}     # from here on a stuck stage still yields the measured bench line
+        wd.stage("tp_check", 90)
+        tpc = tp_check(torch, dist, rank, world, dev, dec, target, wl["target"])
+        if rank == 0:
             line["tp_check"] = tpc
     # ---- the main engines are done: free them before the companion measurements
     dec = None
@@ -577,9 +630,11 @@ def run_ours(args):
         import json as _json
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = _json.load(f)
+        wd.stage("config5", 200)
         c5 = config5(torch, dist, rank, world, dev, args, peaks)
         if rank == 0:
             line["config5"] = c5
+    wd.stage("companions / output", 0)
     if rank == 0:
         if world == 1 and not args.no_companions:
             line["companions"] = companions(torch, dev, peak)

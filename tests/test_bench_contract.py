@@ -1,5 +1,6 @@
 """bench.py's static contract (no GPU): workload naming, parallelism strings, CLI defaults."""
 import importlib.util
+import json
 import os
 import sys
 
@@ -42,3 +43,29 @@ def test_cli_defaults_finish_in_minutes_and_enforce_three_warmups(monkeypatch):
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2"])
     b.main()
     assert seen["impl_called"] == "reference"
+
+
+def test_watchdog_prints_what_it_has_and_leaves():
+    """N > 1: a stage that overruns its budget must not hang the job - rank 0 prints the finished bench line (or an error
+    record when the timed region never finished) and the process exits (bench.Watchdog)."""
+    import subprocess
+    import sys
+    code = """
+import sys, time
+sys.path.insert(0, %r)
+import bench
+wd = bench.Watchdog(0, 8)
+wd.start()
+if sys.argv[1] == "line":
+    wd.line = {"metric": "m", "value": 1.0}
+wd.stage(sys.argv[2], 1)
+time.sleep(20)
+print("NOT REACHED")
+""" % ROOT
+    for have, stage, rc, key in (("none", "setup + prefill", 5, "error"), ("line", "config5", 0, "config5"),
+                                 ("line", "tp_check", 3, "tp_check")):
+        r = subprocess.run([sys.executable, "-c", code, have, stage], capture_output=True, text=True, timeout=60)
+        assert r.returncode == rc, (have, stage, r.returncode, r.stderr[-300:])
+        assert "NOT REACHED" not in r.stdout
+        rec = json.loads(r.stdout.strip().splitlines()[-1])
+        assert key in rec and ("watchdog" in rec or "watchdog" in rec.get("error", ""))
