@@ -78,6 +78,7 @@ class Watchdog(threading.Thread):
         super().__init__(daemon=True)
         self.rank, self.world = rank, world
         self.name_, self.deadline, self.line, self.lock = "start", None, None, threading.Lock()
+        self.printed_rc = None      # set once rank 0 has printed the line: a stuck teardown then just leaves with it
 
     def stage(self, name, budget_s):
         with self.lock:
@@ -95,6 +96,8 @@ class Watchdog(threading.Thread):
             msg = f"stage '{name}' did not finish within its budget on rank {self.rank}"
             sys.stderr.write(f"[bench rank {self.rank}] watchdog: {msg}\n")
             sys.stderr.flush()
+            if self.printed_rc is not None:
+                os._exit(self.printed_rc)
             code = 5
             if line is not None:
                 code = 0 if name == "config5" else 3
@@ -647,6 +650,9 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": r["tokens_per_step"] / r["step_seconds"], "unit": UNIT,
                                     "cores": r["threads"], "kind": "port", "sample": r["sample"], "extrapolated": True}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        wd.printed_rc = 3 if (tpc is not None and rank == 0 and not tpc.get("ok", False)) else 0
+        wd.stage("teardown", 60)
     if comm is not None:
         barrier()
         comm.destroy()
