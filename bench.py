@@ -79,12 +79,18 @@ class Watchdog(threading.Thread):
         self.rank, self.world = rank, world
         self.name_, self.deadline, self.line, self.lock = "start", None, None, threading.Lock()
         self.printed_rc = None      # set once rank 0 has printed the line: a stuck teardown then just leaves with it
+        self.marks = []             # (stage, start time): the line reports how long each stage took
 
     def stage(self, name, budget_s):
         with self.lock:
             self.name_, self.deadline = name, (time.time() + budget_s if budget_s else None)
+            self.marks.append((name, time.time()))
         sys.stderr.write(f"[bench rank {self.rank}] {time.strftime('%H:%M:%S')} stage {name}\n")
         sys.stderr.flush()
+
+    def seconds(self):
+        m = self.marks + [("end", time.time())]
+        return {m[i][0]: round(m[i + 1][1] - m[i][1], 2) for i in range(len(m) - 1)}
 
     def run(self):
         while True:
@@ -649,6 +655,7 @@ def run_ours(args):
             r = spec_step_baseline(tcfg, dcfg, B, k, prefix, T, sample_layers=1, threads=os.cpu_count())
             line["cpu_baseline"] = {"value": r["tokens_per_step"] / r["step_seconds"], "unit": UNIT,
                                     "cores": r["threads"], "kind": "port", "sample": r["sample"], "extrapolated": True}
+        line["stage_seconds"] = wd.seconds()
         print(json.dumps(line), flush=True)
     if world > 1:
         wd.printed_rc = 3 if (tpc is not None and rank == 0 and not tpc.get("ok", False)) else 0
