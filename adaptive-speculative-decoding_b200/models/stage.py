@@ -120,6 +120,15 @@ def validate_gpu_assignment(stages) -> None:
 
 _ORDER = threading.Lock()
 _NEXT_ORDER = [0]
+# one lock per GPU: generations that touch the same device run one after the other.  Kernels of different streams on
+# one SM are not covered by the forward's TMEM hand-over invariant: a 512-column tcgen05.alloc
+# of one stream can hold the allocation permit while a clustered GEMM of the other waits for a sibling that needs it.
+_DEVICE_LOCKS = {}
+
+
+def _device_locks(gpu_ids):
+    with _ORDER:
+        return [_DEVICE_LOCKS.setdefault(int(g), threading.RLock()) for g in sorted(set(int(g) for g in gpu_ids))]
 
 
 class Stage:
@@ -229,6 +238,9 @@ class Stage:
         # a stage's engine also serves as the NEXT stage's draft: whole generations are serialised per engine,
         # locks taken in creation order (smaller stage first) so two stages can never deadlock
         chain = sorted([st for st in (self.draft, self) if st is not None], key=lambda st: st._order)
+        devs = _device_locks([g for st in chain for g in st.gpu_ids])      # device locks first (by index), then stages
+        for d in devs:
+            d.acquire()
         for st in chain:
             st._lock.acquire()
         try:
@@ -246,6 +258,8 @@ class Stage:
         finally:
             for st in reversed(chain):
                 st._lock.release()
+            for d in reversed(devs):
+                d.release()
         stats = {"generation_time_ms": (time.time() - t0) * 1000.0, "draft_tokens_accepted": acc_tok,
                  "decode_steps": steps}
         return texts, lps, stats
