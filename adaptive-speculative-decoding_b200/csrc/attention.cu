@@ -1,4 +1,6 @@
-// Paged-KV attention for the verify step: every (k+1) new position of a sequence is scored against
+// Paged-KV attention for the verify step on the legacy tensor path (mma.sync): the FALLBACK of the tcgen05 / TMEM kernel
+// in attention_tc.cu (engine option attn_impl = 2, default) for head_dim 64 and for more than 128 query rows per
+// (sequence, kv head), and its cross-check (attn_impl = 1).  Every (k+1) new position of a sequence is scored against
 // the paged prefix in ONE pass (causal among the new positions); long contexts (>= 1024 keys per piece) are
 // split over the KV length (flash-decoding) and merged by the last CTA to finish.
 //
