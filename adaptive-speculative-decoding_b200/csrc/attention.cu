@@ -7,9 +7,9 @@
 //   * work item = (sequence, kv head, kv split).  The query tile is all new tokens x the GQA group
 //     of that kv head (rows = q_len * G, e.g. 6 x 5 = 30 for Qwen2.5-32B with k = 5), so each K/V
 //     byte is read from HBM once per sequence, not once per query head;
-//   * QK^T and PV run on tensor cores (mma.sync m16n8k16 bf16 -> fp32; 30..72 query rows cannot fill a
-//     128-row tcgen05 tile and the kernel is bound by the KV stream, not by math), operands staged
-//     with cp.async into XOR-swizzled shared memory and read with ldmatrix;
+//   * QK^T and PV run on tensor cores through mma.sync m16n8k16 bf16 -> fp32 (about an eighth of the tcgen05 rate:
+//     HMMA issue bounds the kernel once the context is long - 0.23 of HBM at a 4096-token prefix against 0.65-0.72
+//     for attention_tc.cu), operands staged with cp.async into XOR-swizzled shared memory and read with ldmatrix;
 //   * with few query rows (draft steps: 7 rows) the warps of a CTA share the rows and split every
 //     64-key tile between them, then merge through shared memory, so that a CTA always has 4+ warps
 //     issuing loads; the last CTA of a (sequence, kv head) to finish merges the kv splits (atomic
