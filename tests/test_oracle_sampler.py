@@ -1,5 +1,5 @@
-"""Sampler oracle (parity unpinned - no reference implementation exists) cross-checked
-against an independent float64 numpy statement of canonical speculative sampling."""
+"""Sampler oracle cross-checked against an independent float64 numpy statement of canonical speculative sampling
+(the reference has no sampler of its own; the pin to vLLM's kernels is tests/test_oracle_sampler_vllm.py)."""
 import numpy as np
 import pytest
 
