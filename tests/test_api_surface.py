@@ -348,3 +348,29 @@ def test_safetensors_round_trip(tmp_path):
         assert back[k].dtype == w[k].dtype and torch.equal(back[k], w[k]), k
     with pytest.raises(FileNotFoundError):
         load_safetensors_dir(str(tmp_path / "nothing"))
+
+
+def test_generations_sharing_a_gpu_take_the_same_device_lock_in_index_order():
+    """Stage.generate serialises generations that touch the same GPU (kernels of different streams are outside the
+    forward's TMEM hand-over invariant): one re-entrant lock per device, handed out sorted by
+    device index so that two cascades with overlapping GPU sets can never wait for each other in a cycle."""
+    import threading
+    from asd_b200.models import stage
+    a = stage._device_locks([3, 1, 3])
+    b = stage._device_locks([1])
+    c = stage._device_locks([5, 3])
+    assert len(a) == 2 and a[0] is b[0] and a[1] is c[0] and len(c) == 2
+    # re-entrant: the draft stage's devices may repeat the target's inside one generation
+    a[0].acquire()
+    assert a[0].acquire(blocking=False)
+    a[0].release()
+    a[0].release()
+    got = []
+    t = threading.Thread(target=lambda: (b[0].acquire(), got.append(1), b[0].release()))
+    a[0].acquire()
+    t.start()
+    t.join(0.2)
+    assert not got              # another thread waits while the device is busy
+    a[0].release()
+    t.join(2)
+    assert got == [1]
