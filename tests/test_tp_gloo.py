@@ -56,11 +56,11 @@ def packed_forward(cfg, w, ids, rank, world, allreduce):
     return x @ w.get("lm_head.weight", w["model.embed_tokens.weight"]).float().T
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, heads=(4, 2, 384)):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.set_num_threads(2)
-    cfg = tiny_config(num_attention_heads=4, num_key_value_heads=2, intermediate_size=384)
+    torch.set_num_threads(1 if world > 2 else 2)
+    cfg = tiny_config(num_attention_heads=heads[0], num_key_value_heads=heads[1], intermediate_size=heads[2])
     w = random_hf_weights(cfg, seed=3)
     ids = torch.randint(0, cfg.vocab_size, (2, 11), generator=torch.Generator().manual_seed(0))
 
@@ -81,6 +81,19 @@ def test_two_rank_tensor_parallel_matches_unsharded():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert len(out) == world and all(v < 1e-4 for v in out.values()), dict(out)
+
+
+@pytest.mark.parametrize("heads", [(40, 8, 1024), (64, 8, 1408)], ids=["32b-ratio", "72b-ratio"])
+def test_eight_rank_split_at_the_target_head_ratios_matches_unsharded(heads):
+    """Over 8 ranks Qwen2.5-32B keeps 5 query heads and ONE kv head per rank (group size 5) and an ffn shard that is a
+    whole number of 64-row gate|up tiles; Qwen2.5-72B keeps 8 query heads, one kv head and an ffn shard of 3696 =
+    57.75 tiles (the last gate|up tile of every rank is padded).  Same ratios on a small model: 40 / 64 heads, 8 kv
+    heads, ffn 8 x 128 / 8 x 176."""
+    world = 8
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out, heads), nprocs=world, join=True)
+    assert len(out) == world and all(v < 2e-4 for v in out.values()), dict(out)
 
 
 def test_single_rank_packing_is_identity():
